@@ -1,0 +1,128 @@
+/* scarplet_b200 — C ABI of the B200-native template-matching hot path.
+ *
+ * The reference (stgl/scarplet 0.1.4) is pure Python and has no FFI; its boundary for
+ * this path is the Python API of scarplet/core.py and the WindowedTemplate plugin
+ * duck type.  Each entry point below replaces the reference interface cited beside
+ * it; scarplet_b200/core.py (the host-side mirror) binds them with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a non-zero status and leaves a
+ * message retrievable with sb_last_error().  A plan is bound to one CUDA device and
+ * is used from one host thread at a time; work is stream-ordered on the plan's
+ * stream.  `*_host` pointers are host memory (copied inside the call), `*_dev`
+ * pointers are device memory on the plan's device.  Inputs are borrowed and never
+ * modified; outputs are caller-allocated.
+ */
+#ifndef SCARPLET_B200_H
+#define SCARPLET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sb_plan sb_plan;
+
+/* One search orientation: the direction of the curvature
+ * (dem.py:68-107 `_calculate_directional_laplacian(alpha)`).  The host passes the
+ * float64 values NumPy computes so the device reproduces them bit for bit. */
+typedef struct sb_angle {
+    double cos_a;   /* np.cos(angle)        */
+    double sin_a;   /* np.sin(angle)        */
+    double cos2_a;  /* np.cos(angle) ** 2   */
+    double sin2_a;  /* np.sin(angle) ** 2   */
+} sb_angle;
+
+enum { SB_KIND_SCARP = 0, SB_KIND_RICKER = 1 };
+enum { SB_ERRMASK_NONE = 0, SB_ERRMASK_XR_LE0 = 1, SB_ERRMASK_XR_GE0 = 2 };
+
+/* One (scale, age, angle) template: what `Template(scale, age, angle, nx, ny, de)`
+ * (core.py:345) plus `.template()`, `.get_window_limits()`, `.get_err_mask()`
+ * (core.py:346, 369-375) determine.  Everything that must be float64-exact is
+ * precomputed by the host. */
+typedef struct sb_template {
+    double cos_t, sin_t;  /* cos/sin of the template's alpha = -angle (WindowedTemplate.py:151) */
+    double c, d;          /* window half-widths (WindowedTemplate.py:63)                     */
+    double k0, k1;        /* scarp: 2*kt**1.5*sqrt(pi), 4*kt;  ricker: pi*f, 0               */
+    double sign;          /* -1 for RightFacingUpperBreakScarp (WindowedTemplate.py:254)    */
+    int32_t kind;         /* SB_KIND_*                                                       */
+    int32_t errmode;      /* SB_ERRMASK_* (WindowedTemplate.py:257-267, 294-304)             */
+    int32_t sy_lo, sy_hi, sx_lo, sx_hi; /* conservative support box, offsets from (ny//2, nx//2) */
+    int32_t i_lo, i_hi, j_lo, j_hi;     /* rows/cols NOT masked by get_window_limits (inclusive) */
+    int32_t angle_id;     /* index into the sb_angle array                                  */
+    int32_t idx;          /* flat result index: tie priority and key into age_of/angle_of   */
+} sb_template;
+
+/* flags for sb_plan_create */
+#define SB_PLAN_DEFAULT 0u
+
+const char* sb_last_error(void);
+/* library / build information: "cuda sm_100a" for the product build */
+const char* sb_build_info(void);
+
+/* Plan = raster geometry + device workspace.  dx2/dy2 are `dx ** 2`, `dy ** 2` as the
+ * host evaluates them (dem.py:95,99).  device < 0 keeps the current device.
+ * stream is a cudaStream_t (0 = the plan creates its own). */
+int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double dy2,
+                   int device, void* stream, unsigned flags);
+int sb_plan_destroy(sb_plan* plan);
+
+/* tuning knobs: key in {"workspace_mb", "max_fft", "force_pad"}; returns 0 if known */
+int sb_plan_set_option(sb_plan* plan, const char* key, long value);
+/* number of kernels launched by this plan so far */
+long sb_plan_launch_count(const sb_plan* plan);
+/* FFT domain and tile grid chosen by the last sweep: out[0..5] = Py, Px, tiles_y, tiles_x, angle batch, template batch */
+int sb_plan_last_geometry(const sb_plan* plan, int* out6);
+
+/* DEM upload (DEMGrid._griddata, float64 row-major ny x nx) and the centred axis
+ * vectors x[nx], y[ny] of WindowedTemplate.py:50-53. */
+int sb_set_dem_host(sb_plan* plan, const double* dem_host);
+int sb_set_dem_dev(sb_plan* plan, const double* dem_dev);
+int sb_set_axes_host(sb_plan* plan, const double* x_host, const double* y_host);
+
+/* DEMGrid._calculate_directional_laplacian (dem.py:68-107): float64 out[ny*nx]. */
+int sb_directional_laplacian(sb_plan* plan, const sb_angle* angle, double* out, int out_is_device);
+
+/* WindowedTemplate.template() (WindowedTemplate.py:159-183, 497-520): float64 out[ny*nx]. */
+int sb_render_template(sb_plan* plan, const sb_template* tmpl, double* out, int out_is_device);
+
+/* core.match_template (core.py:297-377): amp[ny*nx], snr[ny*nx] float64 for one template. */
+int sb_match_template(sb_plan* plan, const sb_angle* angle, const sb_template* tmpl,
+                      double* amp, double* snr, int out_is_device);
+
+/* Best-fit state (running result of core.compare over a sweep). */
+int sb_best_reset(sb_plan* plan);
+
+/* The fan-out of core.calculate_best_fit_parameters / match (core.py:139-195, 266-294)
+ * and the fold of core.compare (core.py:198-243) for a list of templates; accumulates
+ * into the plan's best state (call sb_best_reset first for a fresh search). */
+int sb_sweep(sb_plan* plan, const sb_angle* angles, int n_angles,
+             const sb_template* tmpls, int n_tmpls);
+
+/* Decode the best state to the reference's stack order [amp, age, angle, snr]
+ * (core.py:190-193): out4 is float64[4*ny*nx]; age_of/angle_of are host float64
+ * tables indexed by sb_template.idx (n_idx entries). */
+int sb_finalize(sb_plan* plan, const double* age_of_host, const double* angle_of_host, int n_idx,
+                double* out4, int out_is_device);
+
+/* Raw best state for a cross-GPU merge: device pointers into the plan, ny*nx each. */
+int sb_best_state(sb_plan* plan, float** snr_dev, float** amp_dev, int32_t** idx_dev);
+
+/* core.compare (core.py:198-243) with the reference's exact strict-compare semantics on
+ * float64 host planes: folds (amp, age, angle, snr) into best[4][n].  age/angle may be
+ * NULL, in which case the scalars age_s / angle_s are used. */
+int sb_compare_host(sb_plan* plan, double* best4_host, const double* amp, const double* age,
+                    const double* angle, const double* snr, double age_s, double angle_s);
+
+/* unit-test hook: batched complex64 FFT of length n (power of two, 64..8192) over rows */
+int sb_debug_fft(sb_plan* plan, int n, int rows, const float* in_host, float* out_host, int inverse);
+
+/* synchronise the plan's stream */
+int sb_sync(sb_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCARPLET_B200_H */

@@ -1,0 +1,1 @@
+from . import cache, numpy_fft  # noqa: F401

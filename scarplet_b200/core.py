@@ -1,0 +1,95 @@
+"""Host-side mirror of scarplet/core.py for the template-matching path.
+
+Same function names, positional order, keyword arguments and return layouts as the
+reference; the work is done by the CUDA library behind ``engine.Plan``:
+
+* the Pool fan-out over orientations (core.py:180-183) and the age list
+  comprehension (core.py:288-291) become one batched sweep on the device;
+* ``match_template``'s six FFTs and numexpr passes (core.py:340-375) become the
+  kernels in ``csrc/sb_kernels.cuh``;
+* the serial ``compare`` fold (core.py:227-241) runs in registers inside the last
+  kernel (first maximum wins; see DESIGN.md for the one documented difference on
+  exact float64 ties).
+"""
+import numpy as np
+
+from . import params as P
+from .engine import Plan
+from .templates import device_spec
+
+
+def _grid_fields(data):
+    z = data._griddata
+    return z, data._georef_info.dx, data._georef_info.dy
+
+
+def _plan_for(data, **plan_kwargs):
+    z, dx, dy = _grid_fields(data)
+    ny, nx = z.shape
+    plan = Plan(ny, nx, dx, dy, **plan_kwargs)
+    plan.set_dem(z)
+    return plan
+
+
+def match_template(data, Template, scale, age, angle, **kwargs):
+    """Fit one (scale, age, angle) template to the directional curvature
+    (core.py:297-377).  Returns ``(amp, age, angle, snr)`` with float64 planes."""
+    spec = device_spec(Template)
+    with _plan_for(data) as plan:
+        amp, snr = plan.match_template(spec, scale, age, angle)
+    return amp, age, angle, snr
+
+
+def _sweep(data, Template, scale, ages, ang_max, ang_min, order, plan=None):
+    spec = device_spec(Template)
+    angles = P.search_angles(ang_min, ang_max)
+    own = plan is None
+    if own:
+        plan = _plan_for(data)
+    try:
+        a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, scale, ages, angles, order)
+        plan.reset()
+        plan.sweep(a_rec, t_rec)
+        return plan.finalize(age_of, angle_of)
+    finally:
+        if own:
+            plan.close()
+
+
+def calculate_best_fit_parameters(dem, Template, scale, age, ang_max=np.pi / 2,
+                                  ang_min=-np.pi / 2, **kwargs):
+    """Best amplitude / orientation / SNR at one age over a 1-degree orientation
+    search (core.py:139-195).  Returns ndarray (4, ny, nx): [amp, age, angle, snr]."""
+    return _sweep(dem, Template, scale, [age], ang_max, ang_min, "age_major")
+
+
+def calculate_best_fit_parameters_serial(dem, Template, scale, ang_max=np.pi / 2,
+                                         ang_min=-np.pi / 2, **kwargs):
+    """Flat search over orientations x the 35 default ages (core.py:65-136).
+    Returns ``(best_amp, best_age, best_angle, best_snr)``."""
+    out = _sweep(dem, Template, scale, P.default_ages(), ang_max, ang_min, "angle_major")
+    return out[0], out[1], out[2], out[3]
+
+
+def match(data, Template, **kwargs):
+    """core.py:266-294.  With ``age=`` one orientation search, returned as a stacked
+    ndarray (4, ny, nx); without it the 35-age search, returned like
+    ``compare`` as a tuple of four planes."""
+    if 'age' in kwargs:
+        return calculate_best_fit_parameters(data, Template, **kwargs)
+    scale = kwargs['scale']
+    ang_max = kwargs.get('ang_max', np.pi / 2)
+    ang_min = kwargs.get('ang_min', -np.pi / 2)
+    out = _sweep(data, Template, scale, P.default_ages(), ang_max, ang_min, "age_major")
+    return out[0], out[1], out[2], out[3]
+
+
+def compare(results, ny, nx):
+    """Per-pixel best-SNR select over an iterable of ``(amp, age, angle, snr)``
+    (core.py:198-243), with the reference's exact semantics (strict compares, an
+    exact tie zeroes the pixel), folded on the device in float64."""
+    best = np.zeros((4, ny, nx), dtype=np.float64)
+    with Plan(ny, nx, 1.0, 1.0) as plan:
+        for this_amp, this_age, this_angle, this_snr in results:
+            plan.compare_fold(best, this_amp, this_age, this_angle, this_snr)
+    return best[0], best[1], best[2], best[3]

@@ -1,0 +1,575 @@
+// CUDA kernels of the scarplet template-matching hot path (sm_100a).
+//
+// Schedule (per tile of the raster, FFT domain Py x Px, both powers of two):
+//   k_curv_rows   per search angle: directional Laplacian (float64 stencil on the DEM,
+//                 dem.py:68-107) -> pack curv + i*curv^2 -> row FFT -> Hermitian split
+//   k_curv_cols   per search angle: column FFTs -> F[curv], F[curv^2] half spectra,
+//                 stored column-major so the next kernel reads them coalesced
+//   k_tmpl_rows   per template: evaluate the windowed template (WindowedTemplate.py:
+//                 159-183, 497-520) in float64 on its support box only -> pack
+//                 t + i*M -> row FFT -> Hermitian split (stored column-major)
+//   k_conv_cols   per template: column FFT of the (sparse) template columns ->
+//                 pointwise products with the curvature spectra (core.py:359,363) ->
+//                 inverse column FFT
+//   k_fit_rows    per batch of templates: inverse row FFT (fftshift folded into the
+//                 index map) -> amplitude / SNR (core.py:360-367) -> masks
+//                 (core.py:369-375) -> running best-SNR select (core.py:198-243) kept
+//                 in registers across the batch
+#pragma once
+#include "sb_fft.cuh"
+
+namespace sb {
+
+using sbfft::E;
+
+// ---------------------------------------------------------------------------
+// parameter blocks (plain data, passed by value or read from global memory)
+// ---------------------------------------------------------------------------
+struct Geom {
+    int ny, nx;              // raster
+    int Py, Px;              // FFT domain
+    int oy, ox;              // raster index of the tile's first output pixel
+    int out_ny, out_nx;      // tile output extent
+    int split_y, split_x;    // domain index q maps to signed offset s = q (q < split) or q - P
+    int dly, dlx;            // -(n & 1): circular-shift bookkeeping of fftshift + centring
+    int need_y_lo, need_y_hi;  // signed offsets of the domain rows that carry curvature
+    int need_x_lo, need_x_hi;
+    int kpitch;              // pitch (elements) of half-spectrum rows
+    int syp;                 // pitch (rows) of the per-template support block
+    double dx, dx2, dy2;     // cell size, dx**2, dy**2 as the host computes them
+    double norm;             // 1 / (Px * Py)
+};
+
+struct Angle {               // one search orientation (curvature direction)
+    double ca, sa, ca2, sa2;  // cos, sin, cos**2, sin**2 of the search angle (host float64)
+};
+
+struct Tmpl {                // one (scale, age, angle) template
+    double ca, sa;           // cos / sin of the template's alpha = -angle
+    double c, d;             // half-widths of the curvature window
+    double k0, k1;           // scarp: 2*kt**1.5*sqrt(pi), 4*kt   ricker: pi*f, unused
+    double sign;             // -1 for the right-facing upper-break template
+    int kind;                // 0 scarp family, 1 ricker/channel
+    int errmode;             // 0 none, 1 snr=0 where xr<=0, 2 snr=0 where xr>=0
+    int sy_lo, sy_hi, sx_lo, sx_hi;   // support box, offsets from (ny//2, nx//2)
+    int i_lo, i_hi, j_lo, j_hi;       // un-masked output window (inclusive raster indices)
+    int angle_id;            // index into the sweep's angle list
+    int idx;                 // flat result index (tie priority and decode key)
+};
+
+struct TSum {                // per-template scalars produced by k_tmpl_sums
+    double n_eps;            // sum(M) + eps          core.py:350
+    double ts;               // sum(t**2)             core.py:356
+    double inv_n;            // 1 / n_eps
+    double inv_ts;
+};
+
+constexpr double kEps = 2.220446049250313e-16;   // np.spacing(1), core.py:339
+
+SB_DEVICE int wrap(int v, int n) {
+    int r = v % n;
+    return r < 0 ? r + n : r;
+}
+
+// ---------------------------------------------------------------------------
+// directional Laplacian at one raster pixel (dem.py:68-107), float64, no FMA
+// ---------------------------------------------------------------------------
+SB_DEVICE double zfill(const double* SB_RESTRICT z, long i) {
+    double v = sb_ldg(z + i);
+    return v != v ? 0.0 : v;            // dem.py:85-86
+}
+
+SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int i, int j,
+                              double dx, double dx2, double dy2, const Angle& a) {
+    const long o = (long)i * nx + j;
+    const double zc_raw = sb_ldg(z + o);
+    if (zc_raw != zc_raw) return zc_raw;            // dem.py:105
+    const double zc = zc_raw;
+    double dxx = 0.0, dyy = 0.0, dxy = 0.0;
+    const bool jm = j >= 1, jp = j <= nx - 2, im = i >= 1, ip = i <= ny - 2;
+    double zl = 0.0, zu = 0.0;
+    if (jm) zl = zfill(z, o - 1);
+    if (im) zu = zfill(z, o - nx);
+    if (jm && jp) {
+        const double zr = zfill(z, o + 1);
+        dxx = sb_div(sb_sub(sb_sub(zr, zc), sb_sub(zc, zl)), dx2);       // dem.py:95
+    }
+    if (im && ip) {
+        const double zd = zfill(z, o + nx);
+        dyy = sb_div(sb_sub(sb_sub(zd, zc), sb_sub(zc, zu)), dy2);       // dem.py:99
+    }
+    if (im && jm) {
+        const double zul = zfill(z, o - nx - 1);
+        const double g1 = sb_div(sb_sub(zc, zl), dx);                    // dem.py:88
+        const double g0 = sb_div(sb_sub(zu, zul), dx);
+        dxy = sb_div(sb_sub(g1, g0), dx);                                // dem.py:89
+    }
+    // dem.py:103-104, left to right
+    const double t0 = sb_mul(dxx, a.ca2);
+    const double t1 = sb_mul(sb_mul(sb_mul(2.0, dxy), a.sa), a.ca);
+    const double t2 = sb_mul(dyy, a.sa2);
+    return sb_add(sb_sub(t0, t1), t2);
+}
+
+// ---------------------------------------------------------------------------
+// windowed template value at one pixel (float64)
+// ---------------------------------------------------------------------------
+SB_DEVICE double template_at(const Tmpl& p, double x, double y) {
+    const double xr = sb_add(sb_mul(x, p.ca), sb_mul(y, p.sa));          // WindowedTemplate.py:57
+    const double yr = sb_add(sb_mul(-x, p.sa), sb_mul(y, p.ca));         // :58
+    const bool inside = (fabs(xr) < p.c) && (fabs(yr) < p.d);            // :63
+    if (!inside) return 0.0;
+    double w;
+    if (p.kind == 0) {
+        // (-xr / (2 kt^1.5 sqrt(pi))) * exp(-xr^2 / (4 kt))              :177-178
+        w = sb_mul(sb_div(-xr, p.k0), exp(sb_div(-sb_mul(xr, xr), p.k1)));
+    } else {
+        // (1 - 2 u^2) * exp(-u^2), u = pi f xr                            :514-515
+        const double u = sb_mul(p.k0, xr);
+        const double u2 = sb_mul(u, u);
+        w = sb_mul(sb_sub(1.0, sb_mul(2.0, u2)), exp(-u2));
+    }
+    return p.sign < 0 ? -w : w;
+}
+
+// Hermitian split of the spectrum Z of a packed pair a + i*b of real rows:
+// F[a](k) = (Z(k) + conj Z(-k)) / 2,  F[b](k) = (Z(k) - conj Z(-k)) / (2i).
+// v holds Z[t + q*T]; writes float4 (F[a], F[b]) for k = 0..N/2 to out[k * stride].
+template <int N>
+SB_DEVICE void hermitian_split(const float2 (&v)[E], int t, float2* sm, float4* out, long stride,
+                               bool active) {
+    constexpr int T = N / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) sm[sbfft::pad_index(t + q * T)] = v[q];
+    sb_sync();
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+        const int k = t + q * T;
+        const float2 zp = sm[sbfft::pad_index((N - k) & (N - 1))];
+        const float2 a = v[q];
+        if (active)
+            out[(long)k * stride] = make_float4(0.5f * (a.x + zp.x), 0.5f * (a.y - zp.y),
+                                                0.5f * (a.y + zp.y), -0.5f * (a.x - zp.x));
+    }
+    if (t == 0 && active) {
+        const float2 a = v[E / 2];                 // Nyquist, index N/2 = (E/2)*T
+        out[(long)(N / 2) * stride] = make_float4(a.x, 0.f, a.y, 0.f);
+    }
+    sb_sync();
+}
+
+// ---------------------------------------------------------------------------
+// k_curv_rows<Px>: grid (ceil(need_rows / GP), n_angles)
+// ---------------------------------------------------------------------------
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_curv_rows(Geom g, const double* SB_RESTRICT dem, const Angle* SB_RESTRICT angles, int angle_base,
+            float4* SB_RESTRICT cr, const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    const int need_rows = g.need_y_hi - g.need_y_lo + 1;
+    const int r = sb_bx() * GP + grp;
+    const bool active = r < need_rows;
+    const int a_loc = sb_by();
+    const Angle ang = angles[angle_base + a_loc];
+    float2 v[E];
+    const int gi = wrap(g.oy + g.need_y_lo + (active ? r : 0), g.ny);
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int qx = t + q * T;
+        const int sx = qx < g.split_x ? qx : qx - N;
+        float2 val = make_float2(0.f, 0.f);
+        if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
+            const int gj = wrap(g.ox + sx, g.nx);
+            const double c = curvature_at(dem, g.ny, g.nx, gi, gj, g.dx, g.dx2, g.dy2, ang);
+            val = make_float2((float)c, (float)(c * c));          // curv, curv**2 (core.py:355)
+        }
+        v[q] = val;
+    }
+    sbfft::forward<N>(v, t, sm, tw);
+    float4* out = cr + ((long)a_loc * need_rows + (active ? r : 0)) * g.kpitch;
+    hermitian_split<N>(v, t, sm, out, 1, active);
+}
+
+// ---------------------------------------------------------------------------
+// k_curv_cols<Py>: grid (ceil(KX / GP), n_angles).  Column FFT of both fields.
+// fct layout: [angle][field][kx][Py] float2
+// ---------------------------------------------------------------------------
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_curv_cols(Geom g, const float4* SB_RESTRICT cr, float2* SB_RESTRICT fct,
+            const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    const int KX = g.Px / 2 + 1;
+    const int need_rows = g.need_y_hi - g.need_y_lo + 1;
+    const int kx = sb_bx() * GP + grp;
+    const bool active = kx < KX;
+    const int a_loc = sb_by();
+    const float4* src = cr + (long)a_loc * need_rows * g.kpitch + (active ? kx : 0);
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+        float2 v[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int qy = t + q * T;
+            const int sy = qy < g.split_y ? qy : qy - N;
+            float2 val = make_float2(0.f, 0.f);
+            if (active && sy >= g.need_y_lo && sy <= g.need_y_hi) {
+                const float4 w = sb_ldg(src + (long)(sy - g.need_y_lo) * g.kpitch);
+                val = f == 0 ? make_float2(w.x, w.y) : make_float2(w.z, w.w);
+            }
+            v[q] = val;
+        }
+        sbfft::forward<N>(v, t, sm, tw);
+        if (active) {
+            float2* dst = fct + (((long)a_loc * 2 + f) * KX + kx) * N;
+#pragma unroll
+            for (int q = 0; q < E; ++q) dst[t + q * T] = v[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_tmpl_rows<Px>: grid (ceil(syp / GP), n_templates)
+// trt layout: [template][kx][syp] float4 (F_row[t], F_row[M]);  part: [template][syp] double2
+// ---------------------------------------------------------------------------
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* SB_RESTRICT xvec,
+            const double* SB_RESTRICT yvec, float4* SB_RESTRICT trt, double2* SB_RESTRICT part,
+            const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    const int p_loc = sb_by();
+    const Tmpl p = tmpls[tmpl_base + p_loc];
+    const int rows = p.sy_hi - p.sy_lo + 1;
+    const int r = sb_bx() * GP + grp;
+    const bool active = r < rows;
+    const int KX = N / 2 + 1;
+    const int a0 = g.ny / 2, b0 = g.nx / 2;
+    float2 v[E];
+    double cnt = 0.0, ssq = 0.0;
+    const double y = active ? sb_ldg(yvec + a0 + p.sy_lo + r) : 0.0;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int qx = t + q * T;
+        const int b = qx < N / 2 ? qx : qx - N;
+        float2 val = make_float2(0.f, 0.f);
+        if (active && b >= p.sx_lo && b <= p.sx_hi) {
+            const double w = template_at(p, sb_ldg(xvec + b0 + b), y);
+            if (w != 0.0) {                                   // M = template != 0, core.py:348
+                cnt += 1.0;
+                ssq += w * w;
+                val = make_float2((float)w, 1.f);
+            }
+        }
+        v[q] = val;
+    }
+    // deterministic per-row sums of M and t^2 (two-level, fixed order)
+    {
+        double2* sd = (double2*)sm;
+        sd[t] = make_double2(cnt, ssq);
+        sb_sync();
+        if ((t & 15) == 0) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < 16 && t + i < T; ++i) { a += sd[t + i].x; b += sd[t + i].y; }
+            sd[t] = make_double2(a, b);
+        }
+        sb_sync();
+        if (t == 0) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < T; i += 16) { a += sd[i].x; b += sd[i].y; }
+            if (active) part[(long)p_loc * g.syp + r] = make_double2(a, b);
+        }
+        sb_sync();
+    }
+    sbfft::forward<N>(v, t, sm, tw);
+    float4* out = trt + (long)p_loc * KX * g.syp + (active ? r : 0);
+    hermitian_split<N>(v, t, sm, out, g.syp, active);
+}
+
+// one thread per template: fixed-order sum of the per-row partials
+SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
+                      const double2* SB_RESTRICT part, TSum* SB_RESTRICT sums) {
+    const int p_loc = sb_bx() * 32 + sb_tid();
+    if (p_loc >= count) return;
+    const Tmpl p = tmpls[tmpl_base + p_loc];
+    const int rows = p.sy_hi - p.sy_lo + 1;
+    double n = 0.0, ts = 0.0;
+    for (int r = 0; r < rows; ++r) {
+        const double2 v = part[(long)p_loc * g.syp + r];
+        n += v.x;
+        ts += v.y;
+    }
+    TSum s;
+    s.n_eps = n + kEps;
+    s.ts = ts;
+    s.inv_n = 1.0 / s.n_eps;
+    s.inv_ts = 1.0 / ts;
+    sums[p_loc] = s;
+}
+
+// ---------------------------------------------------------------------------
+// k_conv_cols<Py>: grid (ceil(KX / GP), n_templates)
+// gbuf layout: [template][field][out_ny][kpitch] float2
+// ---------------------------------------------------------------------------
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_conv_cols(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_base,
+            const float4* SB_RESTRICT trt, const float2* SB_RESTRICT fct, float2* SB_RESTRICT gbuf,
+            const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    const int KX = g.Px / 2 + 1;
+    const int kx = sb_bx() * GP + grp;
+    const bool active = kx < KX;
+    const int p_loc = sb_by();
+    const Tmpl p = tmpls[tmpl_base + p_loc];
+    const int a_loc = p.angle_id - angle_base;
+    const float4* src = trt + ((long)p_loc * KX + (active ? kx : 0)) * g.syp;
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+        float2 v[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int qy = t + q * T;
+            const int s = qy < N / 2 ? qy : qy - N;
+            float2 val = make_float2(0.f, 0.f);
+            if (active && s >= p.sy_lo && s <= p.sy_hi) {
+                const float4 w = sb_ldg(src + (s - p.sy_lo));
+                val = f == 0 ? make_float2(w.x, w.y) : make_float2(w.z, w.w);
+            }
+            v[q] = val;
+        }
+        sbfft::forward<N>(v, t, sm, tw);
+        {
+            const float2* spec = fct + (((long)a_loc * 2 + f) * KX + (active ? kx : 0)) * N;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const float2 w = sb_ldg(spec + t + q * T);
+                const float2 pr = sbfft::cmul(v[q], w);           // core.py:359 / :363
+                v[q] = make_float2(pr.y, pr.x);                   // swap: inverse via forward
+            }
+        }
+        sbfft::forward<N>(v, t, sm, tw);
+        if (active) {
+            float2* dst = gbuf + ((long)p_loc * 2 + f) * g.out_ny * g.kpitch + kx;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int m = t + q * T;
+                const int io = (m + g.dly) & (N - 1);
+                if (io < g.out_ny) dst[(long)io * g.kpitch] = make_float2(v[q].y, v[q].x);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_fit_rows<Px>: grid (ceil(out_ny / GP)); loops over the batch of templates
+// ---------------------------------------------------------------------------
+struct FitOut {
+    float* best_snr;         // [ny][nx]
+    float* best_amp;
+    int* best_idx;
+    double* raw_amp;         // single-template mode (match_template): full planes
+    double* raw_snr;
+};
+
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
+           const TSum* SB_RESTRICT sums, const float2* SB_RESTRICT gbuf,
+           const double* SB_RESTRICT xvec, const double* SB_RESTRICT yvec, FitOut out,
+           const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    const int io = sb_bx() * GP + grp;
+    const bool active = io < g.out_ny;
+    const int gi = g.oy + io;
+    const int cta_lo = g.oy + sb_bx() * GP;
+    const int cta_hi = cta_lo + GP - 1;
+    const bool raw = out.raw_amp != nullptr;
+
+    float bs[E], ba[E];
+    int bi[E];
+    int gj[E];
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int m = t + q * T;
+        const int jo = (m + g.dlx) & (N - 1);
+        gj[q] = (active && jo < g.out_nx) ? g.ox + jo : -1;
+        bs[q] = 0.f; ba[q] = 0.f; bi[q] = 0x7fffffff;
+        if (gj[q] >= 0 && !raw) {
+            const long o = (long)gi * g.nx + gj[q];
+            bs[q] = out.best_snr[o];
+            ba[q] = out.best_amp[o];
+            bi[q] = out.best_idx[o];
+        }
+    }
+    const double yv = active ? sb_ldg(yvec + gi) : 0.0;
+
+#pragma unroll 1
+    for (int pl = 0; pl < count; ++pl) {
+        const Tmpl p = tmpls[tmpl_base + pl];
+        if (!raw && (cta_hi < p.i_lo || cta_lo > p.i_hi)) continue;   // whole CTA edge-masked
+        const TSum s = sums[pl];
+        const float2* gt = gbuf + ((long)pl * 2 + 0) * g.out_ny * g.kpitch + (long)(active ? io : 0) * g.kpitch;
+        const float2* gm = gt + (long)g.out_ny * g.kpitch;
+        float2 v[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int k = t + q * T;
+            const bool direct = k <= N / 2;
+            const int kk = direct ? k : N - k;
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            if (active) { a = sb_ldg(gt + kk); b = sb_ldg(gm + kk); }
+            // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
+            const float2 x = direct ? make_float2(a.x - b.y, a.y + b.x)
+                                    : make_float2(a.x + b.y, b.x - a.y);
+            v[q] = make_float2(x.y, x.x);
+        }
+        sbfft::forward<N>(v, t, sm, tw);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            if (gj[q] < 0) continue;
+            const double xc = (double)v[q].y * g.norm;           // Re ifft: xcorr   core.py:359
+            const double t3 = (double)v[q].x * g.norm;           // Im ifft: T3      core.py:363
+            double amp = xc * s.inv_ts;                          // core.py:360
+            const double t1 = s.ts * amp * amp;                  // core.py:362
+            const double err = s.inv_n * (t1 - 2.0 * amp * xc + t3) + kEps;   // core.py:366
+            double snr = fabs(t1 / err);                         // core.py:367
+            if (p.errmode != 0) {                                // core.py:369-371
+                const double xr = sb_add(sb_mul(sb_ldg(xvec + gj[q]), p.ca), sb_mul(yv, p.sa));
+                if ((p.errmode == 1 && xr <= 0.0) || (p.errmode == 2 && xr >= 0.0)) snr = 0.0;
+            }
+            if (gi < p.i_lo || gi > p.i_hi || gj[q] < p.j_lo || gj[q] > p.j_hi) {   // core.py:373-375
+                amp = 0.0;
+                snr = 0.0;
+            }
+            if (raw) {
+                const long o = (long)gi * g.nx + gj[q];
+                out.raw_amp[o] = amp;
+                out.raw_snr[o] = snr;
+            } else {
+                const float sf = (float)snr;
+                // first maximum wins (core.py:230-240); equal positive SNRs resolve to the
+                // lower flat index so the result does not depend on batch order
+                if (sf > bs[q] || (sf == bs[q] && sf > 0.f && p.idx < bi[q])) {
+                    bs[q] = sf;
+                    ba[q] = (float)amp;
+                    bi[q] = p.idx;
+                }
+            }
+        }
+    }
+    if (!raw) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            if (gj[q] < 0) continue;
+            const long o = (long)gi * g.nx + gj[q];
+            out.best_snr[o] = bs[q];
+            out.best_amp[o] = ba[q];
+            out.best_idx[o] = bi[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// elementwise kernels
+// ---------------------------------------------------------------------------
+SB_GLOBAL k_best_init(long n, float* snr, float* amp, int* idx) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i < n) { snr[i] = 0.f; amp[i] = 0.f; idx[i] = 0x7fffffff; }
+}
+
+// decode the best state into the reference's [amp, age, angle, snr] float64 planes
+SB_GLOBAL k_finalize(long n, const float* SB_RESTRICT snr, const float* SB_RESTRICT amp,
+                     const int* SB_RESTRICT idx, const double* SB_RESTRICT age_of,
+                     const double* SB_RESTRICT angle_of, double* SB_RESTRICT out4) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    const float s = snr[i];
+    const int k = idx[i];
+    const bool hit = s > 0.f && k != 0x7fffffff;
+    out4[i] = hit ? (double)amp[i] : 0.0;
+    out4[n + i] = hit ? age_of[k] : 0.0;
+    out4[2 * n + i] = hit ? angle_of[k] : 0.0;
+    out4[3 * n + i] = hit ? (double)s : 0.0;
+}
+
+// full-raster directional Laplacian in float64 (DEMGrid._calculate_directional_laplacian)
+SB_GLOBAL k_laplacian(int ny, int nx, const double* SB_RESTRICT dem, double dx, double dx2,
+                      double dy2, Angle a, double* SB_RESTRICT out) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= (long)ny * nx) return;
+    out[i] = curvature_at(dem, ny, nx, (int)(i / nx), (int)(i % nx), dx, dx2, dy2, a);
+}
+
+// full-raster template in float64 (WindowedTemplate.template())
+SB_GLOBAL k_render_template(int ny, int nx, Tmpl p, const double* SB_RESTRICT xvec,
+                            const double* SB_RESTRICT yvec, double* SB_RESTRICT out) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= (long)ny * nx) return;
+    const int a = (int)(i / nx) - ny / 2, b = (int)(i % nx) - nx / 2;
+    double w = 0.0;
+    if (a >= p.sy_lo && a <= p.sy_hi && b >= p.sx_lo && b <= p.sx_hi)
+        w = template_at(p, xvec[b + nx / 2], yvec[a + ny / 2]);
+    out[i] = w;
+}
+
+// core.compare (core.py:198-243) on full planes with the reference's exact
+// semantics (strict compares; an exact tie zeroes the pixel).  this_age / this_angle
+// are scalars when the pointers are null.
+SB_GLOBAL k_compare(long n, double* best_amp, double* best_age, double* best_angle, double* best_snr,
+                    const double* SB_RESTRICT amp, const double* SB_RESTRICT age_p,
+                    const double* SB_RESTRICT angle_p, const double* SB_RESTRICT snr,
+                    double age_s, double angle_s) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    const double bs = best_snr[i], ts = snr[i];
+    const double keep = bs > ts ? 1.0 : 0.0, take = bs < ts ? 1.0 : 0.0;
+    const double ta = amp[i];
+    const double tg = age_p ? age_p[i] : age_s;
+    const double tn = angle_p ? angle_p[i] : angle_s;
+    best_amp[i] = sb_add(sb_mul(keep, best_amp[i]), sb_mul(take, ta));
+    best_age[i] = sb_add(sb_mul(keep, best_age[i]), sb_mul(take, tg));
+    best_angle[i] = sb_add(sb_mul(keep, best_angle[i]), sb_mul(take, tn));
+    best_snr[i] = sb_add(sb_mul(keep, bs), sb_mul(take, ts));
+}
+
+// debugging / unit-test kernel: batched forward FFT of length N, rows of `in`
+template <int N>
+SB_GLOBAL k_fft_rows(int rows, const float2* SB_RESTRICT in, float2* SB_RESTRICT outp, int inverse,
+                     const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    const int r = sb_bx() * GP + grp;
+    const bool active = r < rows;
+    float2 v[E];
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        float2 a = active ? in[(long)r * N + t + q * T] : make_float2(0.f, 0.f);
+        v[q] = inverse ? make_float2(a.y, a.x) : a;
+    }
+    sbfft::forward<N>(v, t, sm, tw);
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < E; ++q)
+            outp[(long)r * N + t + q * T] = inverse ? make_float2(v[q].y, v[q].x) : v[q];
+    }
+}
+
+}  // namespace sb

@@ -1,0 +1,667 @@
+// Host side of the C ABI declared in include/scarplet_b200.h: plan, workspace,
+// tile / batch scheduling and kernel launches.  No torch types, no CPU compute path.
+#include "../../include/scarplet_b200.h"
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "sb_kernels.cuh"
+
+static_assert(sizeof(sb_template) == sizeof(sb::Tmpl), "sb_template / sb::Tmpl layout");
+static_assert(sizeof(sb_angle) == sizeof(sb::Angle), "sb_angle / sb::Angle layout");
+static_assert(offsetof(sb_template, kind) == offsetof(sb::Tmpl, kind), "layout");
+static_assert(offsetof(sb_template, idx) == offsetof(sb::Tmpl, idx), "layout");
+static_assert(offsetof(sb_template, i_lo) == offsetof(sb::Tmpl, i_lo), "layout");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+
+#define SB_TRY(expr)                                                                      \
+    do {                                                                                  \
+        int _e = (expr);                                                                  \
+        if (_e != 0)                                                                      \
+            return fail(std::string(#expr) + ": " + sb_rt_error_string(_e) + " (" +       \
+                        std::to_string(_e) + ")");                                        \
+    } while (0)
+
+#define SB_OK(expr)                     \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != 0) return _s;         \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+int next_pow2(long n) {
+    long p = 1;
+    while (p < n) p <<= 1;
+    return (int)p;
+}
+constexpr int kMinFft = 128;
+constexpr int kMaxFftSupported = 8192;
+
+struct AxisPlan {
+    int P = 0;          // FFT length
+    int tiles = 1;
+    int tile_out = 0;   // output pixels per tile (last tile may be shorter)
+    int lo = 0, hi = 0; // support offsets
+    bool periodic = false;
+};
+
+}  // namespace
+
+struct sb_plan {
+    int ny = 0, nx = 0;
+    double dx = 1, dx2 = 1, dy2 = 1;
+    int device = 0;
+    sb_stream_t stream = 0;
+    bool own_stream = false;
+    double* d_dem = nullptr;
+    bool own_dem = false;
+    double* d_x = nullptr;
+    double* d_y = nullptr;
+    float* d_bsnr = nullptr;
+    float* d_bamp = nullptr;
+    int* d_bidx = nullptr;
+    std::map<int, float2*> tw;
+    Buf cr, fct, trt, part, gbuf, sums, tmpls, angles, tables, raw;
+    long launches = 0;
+    long workspace_mb = 8192;
+    int max_fft = kMaxFftSupported;
+    int force_pad = 0;
+    int last_geom[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int ensure(Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) sb_rt_free(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    SB_TRY(sb_rt_malloc(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+void release(Buf& b) {
+    if (b.p) sb_rt_free(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int twiddles(sb_plan* pl, int n, const float2** out) {
+    auto it = pl->tw.find(n);
+    if (it != pl->tw.end()) {
+        *out = it->second;
+        return 0;
+    }
+    int count = 0;
+    {   // same stage walk as sbfft::fill_twiddles
+        int ns = 1;
+        for (int s = 0; n > ns; ++s) {
+            int rest = n / ns, r = rest >= 16 ? 16 : rest;
+            if (s > 0) count += (r - 1) * ns;
+            ns *= r;
+        }
+    }
+    std::vector<float2> host(std::max(count, 1));
+    sbfft::fill_twiddles(n, host.data());
+    void* d = nullptr;
+    SB_TRY(sb_rt_malloc(&d, host.size() * sizeof(float2)));
+    SB_TRY(sb_rt_h2d(d, host.data(), host.size() * sizeof(float2), pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    pl->tw[n] = (float2*)d;
+    *out = (float2*)d;
+    return 0;
+}
+
+template <typename F>
+int dispatch_n(int n, F&& f) {
+    switch (n) {
+        case 128: return f(std::integral_constant<int, 128>{});
+        case 256: return f(std::integral_constant<int, 256>{});
+        case 512: return f(std::integral_constant<int, 512>{});
+        case 1024: return f(std::integral_constant<int, 1024>{});
+        case 2048: return f(std::integral_constant<int, 2048>{});
+        case 4096: return f(std::integral_constant<int, 4096>{});
+        case 8192: return f(std::integral_constant<int, 8192>{});
+        default: return fail("unsupported FFT length " + std::to_string(n));
+    }
+}
+
+template <int N>
+struct Shape {
+    static constexpr int T = N / sbfft::E;
+    static constexpr int threads = T > 256 ? T : 256;
+    static constexpr int GP = threads / T;
+    static constexpr size_t smem = (size_t)GP * sbfft::padded_len(N) * sizeof(float2);
+};
+
+#ifndef SB_EMU
+template <typename K>
+int allow_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        SB_TRY((int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+#define SB_ALLOW_SMEM(kern, bytes) SB_OK(allow_smem(kern, bytes))
+#else
+#define SB_ALLOW_SMEM(kern, bytes)
+#endif
+
+int check_launch(sb_plan* pl, const char* what) {
+    pl->launches++;
+    int e = sb_rt_last_error();
+    if (e != 0) return fail(std::string(what) + ": " + sb_rt_error_string(e));
+    return 0;
+}
+
+int div_up(long a, long b) { return (int)((a + b - 1) / b); }
+
+// choose FFT length / tiling along one axis
+int plan_axis(const sb_plan* pl, int n, int lo, int hi, AxisPlan* ax) {
+    lo = std::min(lo, 0);
+    hi = std::max(hi, 0);
+    ax->lo = lo;
+    ax->hi = hi;
+    const int ext = hi - lo + 1;
+    const int max_fft = std::min(pl->max_fft, kMaxFftSupported);
+    if (is_pow2(n) && n >= kMinFft && n <= max_fft && !pl->force_pad) {
+        ax->P = n;
+        ax->tiles = 1;
+        ax->tile_out = n;
+        ax->periodic = true;
+        return 0;
+    }
+    ax->periodic = false;
+    long best_cost = -1;
+    for (int P = kMinFft; P <= max_fft; P <<= 1) {
+        if (P < ext + 1 || hi >= P / 2 || -lo > P / 2) continue;
+        const int cap = P - ext;
+        if (cap < 1) continue;
+        const int tiles = div_up(n, cap);
+        const long cost = (long)tiles * P;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            ax->P = P;
+            ax->tiles = tiles;
+            ax->tile_out = div_up(n, tiles);
+        }
+    }
+    if (best_cost < 0)
+        return fail("template support (" + std::to_string(ext) + " px) does not fit max_fft=" +
+                    std::to_string(max_fft));
+    return 0;
+}
+
+void fill_axis(const AxisPlan& ax, int n, int tile, int* o, int* out_n, int* split, int* dl,
+               int* need_lo, int* need_hi) {
+    *dl = -(n & 1);
+    *o = tile * ax.tile_out;
+    *out_n = std::min(ax.tile_out, n - *o);
+    if (ax.periodic) {
+        *split = ax.P;
+        *need_lo = 0;
+        *need_hi = ax.P - 1;
+    } else {
+        *split = *out_n - *dl - ax.lo + 1;
+        *need_lo = -*dl - ax.hi;
+        *need_hi = *out_n - 1 - *dl - ax.lo;
+    }
+}
+
+struct SweepOut {
+    double* raw_amp = nullptr;
+    double* raw_snr = nullptr;
+};
+
+int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in,
+              int n_tmpls, SweepOut so) {
+    if (!pl->d_dem) return fail("no DEM set (sb_set_dem_host / sb_set_dem_dev)");
+    if (!pl->d_x || !pl->d_y) return fail("no axis vectors set (sb_set_axes_host)");
+    if (n_tmpls <= 0 || n_angles <= 0) return 0;
+
+    // order templates by search angle so that each curvature spectrum is built once
+    std::vector<sb_template> tm(tmpls_in, tmpls_in + n_tmpls);
+    std::stable_sort(tm.begin(), tm.end(),
+                     [](const sb_template& a, const sb_template& b) { return a.angle_id < b.angle_id; });
+    int lo_y = 0, hi_y = 0, lo_x = 0, hi_x = 0, syp = 1;
+    for (auto& t : tm) {
+        if (t.angle_id < 0 || t.angle_id >= n_angles) return fail("template angle_id out of range");
+        if (t.sy_hi < t.sy_lo || t.sx_hi < t.sx_lo) return fail("empty template support box");
+        if (t.sy_lo < -(pl->ny / 2) || t.sy_hi > pl->ny - 1 - pl->ny / 2 || t.sx_lo < -(pl->nx / 2) ||
+            t.sx_hi > pl->nx - 1 - pl->nx / 2)
+            return fail("template support box exceeds the raster");
+        lo_y = std::min(lo_y, t.sy_lo);
+        hi_y = std::max(hi_y, t.sy_hi);
+        lo_x = std::min(lo_x, t.sx_lo);
+        hi_x = std::max(hi_x, t.sx_hi);
+        syp = std::max(syp, t.sy_hi - t.sy_lo + 1);
+    }
+    AxisPlan ay, ax;
+    SB_OK(plan_axis(pl, pl->ny, lo_y, hi_y, &ay));
+    SB_OK(plan_axis(pl, pl->nx, lo_x, hi_x, &ax));
+    const int Py = ay.P, Px = ax.P;
+    const int KX = Px / 2 + 1;
+    const int kpitch = Px / 2 + 8;
+
+    const float2 *twy = nullptr, *twx = nullptr;
+    SB_OK(twiddles(pl, Py, &twy));
+    SB_OK(twiddles(pl, Px, &twx));
+
+    // batch sizes from the workspace budget
+    const int need_rows_max = ay.periodic ? Py : std::min(Py, ay.tile_out + (hi_y - lo_y) + 2);
+    const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(float4) + (size_t)2 * KX * Py * sizeof(float2);
+    const size_t per_tmpl = (size_t)KX * syp * sizeof(float4) + (size_t)2 * ay.tile_out * kpitch * sizeof(float2) +
+                            (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
+    const size_t budget = (size_t)pl->workspace_mb << 20;
+    // templates per angle (max) decides the split of the budget
+    std::vector<int> first(n_angles + 1, 0);
+    for (auto& t : tm) first[t.angle_id + 1]++;
+    int max_per_angle = 1;
+    for (int a = 0; a < n_angles; ++a) {
+        max_per_angle = std::max(max_per_angle, first[a + 1]);
+        first[a + 1] += first[a];
+    }
+    int Bt = (int)std::max<size_t>(1, std::min<size_t>(64, (budget * 6 / 10) / per_tmpl));
+    int Ba = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_angles, (budget * 4 / 10) / per_angle));
+    Ba = std::min(Ba, 64);
+    if (max_per_angle == 1) Bt = std::min(Bt, Ba), Ba = std::min(Ba, Bt);
+    Bt = std::min(Bt, n_tmpls);
+
+    SB_OK(ensure(pl->cr, (size_t)Ba * need_rows_max * kpitch * sizeof(float4)));
+    SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(float2)));
+    SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(float4)));
+    SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
+    SB_OK(ensure(pl->gbuf, (size_t)Bt * 2 * ay.tile_out * kpitch * sizeof(float2)));
+    SB_OK(ensure(pl->sums, (size_t)Bt * sizeof(sb::TSum)));
+    SB_OK(ensure(pl->tmpls, (size_t)n_tmpls * sizeof(sb::Tmpl)));
+    SB_OK(ensure(pl->angles, (size_t)n_angles * sizeof(sb::Angle)));
+    SB_TRY(sb_rt_h2d(pl->tmpls.p, tm.data(), (size_t)n_tmpls * sizeof(sb::Tmpl), pl->stream));
+    SB_TRY(sb_rt_h2d(pl->angles.p, angles, (size_t)n_angles * sizeof(sb::Angle), pl->stream));
+    // the host vectors must outlive the async copies
+    SB_TRY(sb_rt_sync(pl->stream));
+
+    pl->last_geom[0] = Py; pl->last_geom[1] = Px; pl->last_geom[2] = ay.tiles; pl->last_geom[3] = ax.tiles;
+    pl->last_geom[4] = Ba; pl->last_geom[5] = Bt;
+
+    const sb::Tmpl* d_tm = (const sb::Tmpl*)pl->tmpls.p;
+    const sb::Angle* d_an = (const sb::Angle*)pl->angles.p;
+    sb::FitOut fo;
+    fo.best_snr = pl->d_bsnr; fo.best_amp = pl->d_bamp; fo.best_idx = pl->d_bidx;
+    fo.raw_amp = so.raw_amp; fo.raw_snr = so.raw_snr;
+
+    for (int ty = 0; ty < ay.tiles; ++ty)
+        for (int tx = 0; tx < ax.tiles; ++tx) {
+            sb::Geom g;
+            g.ny = pl->ny; g.nx = pl->nx; g.Py = Py; g.Px = Px;
+            fill_axis(ay, pl->ny, ty, &g.oy, &g.out_ny, &g.split_y, &g.dly, &g.need_y_lo, &g.need_y_hi);
+            fill_axis(ax, pl->nx, tx, &g.ox, &g.out_nx, &g.split_x, &g.dlx, &g.need_x_lo, &g.need_x_hi);
+            g.kpitch = kpitch; g.syp = syp;
+            g.dx = pl->dx; g.dx2 = pl->dx2; g.dy2 = pl->dy2;
+            g.norm = 1.0 / ((double)Px * (double)Py);
+            const int need_rows = g.need_y_hi - g.need_y_lo + 1;
+
+            for (int a0 = 0; a0 < n_angles; a0 += Ba) {
+                const int a1 = std::min(n_angles, a0 + Ba);
+                const int p0 = first[a0], p1 = first[a1];
+                if (p1 == p0) continue;
+                SB_OK(dispatch_n(Px, [&](auto nn) {
+                    constexpr int N = decltype(nn)::value;
+                    using S = Shape<N>;
+                    SB_ALLOW_SMEM(sb::k_curv_rows<N>, S::smem);
+                    SB_LAUNCH(sb::k_curv_rows<N>, dim3(div_up(need_rows, S::GP), a1 - a0), dim3(S::threads),
+                              S::smem, pl->stream, g, (const double*)pl->d_dem, d_an, a0, (float4*)pl->cr.p, twx);
+                    return check_launch(pl, "k_curv_rows");
+                }));
+                SB_OK(dispatch_n(Py, [&](auto nn) {
+                    constexpr int N = decltype(nn)::value;
+                    using S = Shape<N>;
+                    SB_ALLOW_SMEM(sb::k_curv_cols<N>, S::smem);
+                    SB_LAUNCH(sb::k_curv_cols<N>, dim3(div_up(KX, S::GP), a1 - a0), dim3(S::threads), S::smem,
+                              pl->stream, g, (const float4*)pl->cr.p, (float2*)pl->fct.p, twy);
+                    return check_launch(pl, "k_curv_cols");
+                }));
+                for (int pb = p0; pb < p1; pb += Bt) {
+                    const int cnt = std::min(Bt, p1 - pb);
+                    SB_OK(dispatch_n(Px, [&](auto nn) {
+                        constexpr int N = decltype(nn)::value;
+                        using S = Shape<N>;
+                        SB_ALLOW_SMEM(sb::k_tmpl_rows<N>, S::smem);
+                        SB_LAUNCH(sb::k_tmpl_rows<N>, dim3(div_up(syp, S::GP), cnt), dim3(S::threads), S::smem,
+                                  pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
+                                  (float4*)pl->trt.p, (double2*)pl->part.p, twx);
+                        return check_launch(pl, "k_tmpl_rows");
+                    }));
+                    SB_LAUNCH(sb::k_tmpl_sums, dim3(div_up(cnt, 32)), dim3(32), 0, pl->stream, g, d_tm, pb, cnt,
+                              (const double2*)pl->part.p, (sb::TSum*)pl->sums.p);
+                    SB_OK(check_launch(pl, "k_tmpl_sums"));
+                    SB_OK(dispatch_n(Py, [&](auto nn) {
+                        constexpr int N = decltype(nn)::value;
+                        using S = Shape<N>;
+                        SB_ALLOW_SMEM(sb::k_conv_cols<N>, S::smem);
+                        SB_LAUNCH(sb::k_conv_cols<N>, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem,
+                                  pl->stream, g, d_tm, pb, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
+                                  (float2*)pl->gbuf.p, twy);
+                        return check_launch(pl, "k_conv_cols");
+                    }));
+                    SB_OK(dispatch_n(Px, [&](auto nn) {
+                        constexpr int N = decltype(nn)::value;
+                        using S = Shape<N>;
+                        SB_ALLOW_SMEM(sb::k_fit_rows<N>, S::smem);
+                        SB_LAUNCH(sb::k_fit_rows<N>, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
+                                  pl->stream, g, d_tm, pb, cnt, (const sb::TSum*)pl->sums.p,
+                                  (const float2*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
+                        return check_launch(pl, "k_fit_rows");
+                    }));
+                }
+            }
+        }
+    return 0;
+}
+
+int copy_out(sb_plan* pl, double* dst, const double* src_dev, size_t count, int out_is_device) {
+    if (out_is_device)
+        SB_TRY(sb_rt_d2d(dst, src_dev, count * sizeof(double), pl->stream));
+    else
+        SB_TRY(sb_rt_d2h(dst, src_dev, count * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sb_last_error(void) { return g_err.c_str(); }
+
+const char* sb_build_info(void) {
+#ifdef SB_EMU
+    return "cpu-emulator (test infrastructure)";
+#else
+    return "cuda sm_100a";
+#endif
+}
+
+int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double dy2, int device,
+                   void* stream, unsigned flags) {
+    (void)flags;
+    if (!plan || ny < 3 || nx < 3) return fail("sb_plan_create: bad arguments");
+    sb_plan* pl = new sb_plan();
+    pl->ny = ny; pl->nx = nx; pl->dx = dx; pl->dx2 = dx2; pl->dy2 = dy2;
+#ifndef SB_EMU
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        delete pl;
+        return fail("no CUDA device available: scarplet_b200 has no CPU path");
+    }
+    if (device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) { delete pl; return fail("cudaSetDevice failed"); }
+    }
+    cudaGetDevice(&pl->device);
+    if (stream) {
+        pl->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete pl;
+            return fail("cudaStreamCreate failed");
+        }
+        pl->own_stream = true;
+    }
+#else
+    (void)device; (void)stream;
+#endif
+    const size_t n = (size_t)ny * nx;
+    int e = 0;
+    e |= sb_rt_malloc((void**)&pl->d_bsnr, n * sizeof(float));
+    e |= sb_rt_malloc((void**)&pl->d_bamp, n * sizeof(float));
+    e |= sb_rt_malloc((void**)&pl->d_bidx, n * sizeof(int));
+    if (e) { sb_plan_destroy(pl); return fail("sb_plan_create: out of device memory"); }
+    *plan = pl;
+    return sb_best_reset(pl);
+}
+
+int sb_plan_destroy(sb_plan* pl) {
+    if (!pl) return 0;
+#ifndef SB_EMU
+    cudaSetDevice(pl->device);
+#endif
+    sb_rt_sync(pl->stream);
+    if (pl->own_dem && pl->d_dem) sb_rt_free(pl->d_dem);
+    if (pl->d_x) sb_rt_free(pl->d_x);
+    if (pl->d_y) sb_rt_free(pl->d_y);
+    if (pl->d_bsnr) sb_rt_free(pl->d_bsnr);
+    if (pl->d_bamp) sb_rt_free(pl->d_bamp);
+    if (pl->d_bidx) sb_rt_free(pl->d_bidx);
+    for (auto& kv : pl->tw) sb_rt_free(kv.second);
+    for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->tmpls, &pl->angles,
+                   &pl->tables, &pl->raw})
+        release(*b);
+#ifndef SB_EMU
+    if (pl->own_stream) cudaStreamDestroy(pl->stream);
+#endif
+    delete pl;
+    return 0;
+}
+
+int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
+    if (!pl || !key) return fail("sb_plan_set_option: null");
+    std::string k(key);
+    if (k == "workspace_mb") { pl->workspace_mb = std::max(64L, value); return 0; }
+    if (k == "max_fft") {
+        if (!is_pow2((int)value) || value < kMinFft || value > kMaxFftSupported)
+            return fail("max_fft must be a power of two in [128, 8192]");
+        pl->max_fft = (int)value;
+        return 0;
+    }
+    if (k == "force_pad") { pl->force_pad = value != 0; return 0; }
+    return fail("unknown option " + k);
+}
+
+long sb_plan_launch_count(const sb_plan* pl) { return pl ? pl->launches : 0; }
+
+int sb_plan_last_geometry(const sb_plan* pl, int* out6) {
+    if (!pl || !out6) return fail("null");
+    for (int i = 0; i < 6; ++i) out6[i] = pl->last_geom[i];
+    return 0;
+}
+
+int sb_set_dem_host(sb_plan* pl, const double* dem_host) {
+    if (!pl || !dem_host) return fail("sb_set_dem_host: null");
+    const size_t bytes = (size_t)pl->ny * pl->nx * sizeof(double);
+    if (!pl->own_dem || !pl->d_dem) {
+        pl->d_dem = nullptr;
+        SB_TRY(sb_rt_malloc((void**)&pl->d_dem, bytes));
+        pl->own_dem = true;
+    }
+    SB_TRY(sb_rt_h2d(pl->d_dem, dem_host, bytes, pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_set_dem_dev(sb_plan* pl, const double* dem_dev) {
+    if (!pl || !dem_dev) return fail("sb_set_dem_dev: null");
+    if (pl->own_dem && pl->d_dem) sb_rt_free(pl->d_dem);
+    pl->own_dem = false;
+    pl->d_dem = const_cast<double*>(dem_dev);
+    return 0;
+}
+
+int sb_set_axes_host(sb_plan* pl, const double* x_host, const double* y_host) {
+    if (!pl || !x_host || !y_host) return fail("sb_set_axes_host: null");
+    if (!pl->d_x) SB_TRY(sb_rt_malloc((void**)&pl->d_x, (size_t)pl->nx * sizeof(double)));
+    if (!pl->d_y) SB_TRY(sb_rt_malloc((void**)&pl->d_y, (size_t)pl->ny * sizeof(double)));
+    SB_TRY(sb_rt_h2d(pl->d_x, x_host, (size_t)pl->nx * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_h2d(pl->d_y, y_host, (size_t)pl->ny * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_directional_laplacian(sb_plan* pl, const sb_angle* angle, double* out, int out_is_device) {
+    if (!pl || !angle || !out) return fail("sb_directional_laplacian: null");
+    if (!pl->d_dem) return fail("no DEM set");
+    const long n = (long)pl->ny * pl->nx;
+    double* dst = out;
+    if (!out_is_device) {
+        SB_OK(ensure(pl->raw, (size_t)n * 2 * sizeof(double)));
+        dst = (double*)pl->raw.p;
+    }
+    sb::Angle a;
+    a.ca = angle->cos_a; a.sa = angle->sin_a; a.ca2 = angle->cos2_a; a.sa2 = angle->sin2_a;
+    SB_LAUNCH(sb::k_laplacian, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx,
+              (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, a, dst);
+    SB_OK(check_launch(pl, "k_laplacian"));
+    if (!out_is_device) return copy_out(pl, out, dst, (size_t)n, 0);
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_render_template(sb_plan* pl, const sb_template* tmpl, double* out, int out_is_device) {
+    if (!pl || !tmpl || !out) return fail("sb_render_template: null");
+    if (!pl->d_x || !pl->d_y) return fail("no axis vectors set");
+    const long n = (long)pl->ny * pl->nx;
+    double* dst = out;
+    if (!out_is_device) {
+        SB_OK(ensure(pl->raw, (size_t)n * 2 * sizeof(double)));
+        dst = (double*)pl->raw.p;
+    }
+    sb::Tmpl t;
+    std::memcpy(&t, tmpl, sizeof(t));
+    SB_LAUNCH(sb::k_render_template, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx, t,
+              (const double*)pl->d_x, (const double*)pl->d_y, dst);
+    SB_OK(check_launch(pl, "k_render_template"));
+    if (!out_is_device) return copy_out(pl, out, dst, (size_t)n, 0);
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_match_template(sb_plan* pl, const sb_angle* angle, const sb_template* tmpl, double* amp, double* snr,
+                      int out_is_device) {
+    if (!pl || !angle || !tmpl || !amp || !snr) return fail("sb_match_template: null");
+    const size_t n = (size_t)pl->ny * pl->nx;
+    SweepOut so;
+    if (out_is_device) {
+        so.raw_amp = amp;
+        so.raw_snr = snr;
+    } else {
+        SB_OK(ensure(pl->raw, n * 2 * sizeof(double)));
+        so.raw_amp = (double*)pl->raw.p;
+        so.raw_snr = so.raw_amp + n;
+    }
+    sb_template t = *tmpl;
+    t.angle_id = 0;
+    SB_OK(run_sweep(pl, angle, 1, &t, 1, so));
+    if (!out_is_device) {
+        SB_TRY(sb_rt_d2h(amp, so.raw_amp, n * sizeof(double), pl->stream));
+        SB_TRY(sb_rt_d2h(snr, so.raw_snr, n * sizeof(double), pl->stream));
+    }
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_best_reset(sb_plan* pl) {
+    if (!pl) return fail("null plan");
+    const long n = (long)pl->ny * pl->nx;
+    SB_LAUNCH(sb::k_best_init, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, pl->d_bsnr, pl->d_bamp,
+              pl->d_bidx);
+    return check_launch(pl, "k_best_init");
+}
+
+int sb_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls, int n_tmpls) {
+    if (!pl || !angles || !tmpls) return fail("sb_sweep: null");
+    return run_sweep(pl, angles, n_angles, tmpls, n_tmpls, SweepOut());
+}
+
+int sb_finalize(sb_plan* pl, const double* age_of_host, const double* angle_of_host, int n_idx, double* out4,
+                int out_is_device) {
+    if (!pl || !age_of_host || !angle_of_host || !out4 || n_idx <= 0) return fail("sb_finalize: bad arguments");
+    const long n = (long)pl->ny * pl->nx;
+    SB_OK(ensure(pl->tables, (size_t)2 * n_idx * sizeof(double)));
+    double* d_age = (double*)pl->tables.p;
+    double* d_ang = d_age + n_idx;
+    SB_TRY(sb_rt_h2d(d_age, age_of_host, (size_t)n_idx * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_h2d(d_ang, angle_of_host, (size_t)n_idx * sizeof(double), pl->stream));
+    double* dst = out4;
+    if (!out_is_device) {
+        SB_OK(ensure(pl->raw, (size_t)n * 4 * sizeof(double)));
+        dst = (double*)pl->raw.p;
+    }
+    SB_LAUNCH(sb::k_finalize, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr,
+              (const float*)pl->d_bamp, (const int*)pl->d_bidx, (const double*)d_age, (const double*)d_ang, dst);
+    SB_OK(check_launch(pl, "k_finalize"));
+    if (!out_is_device) return copy_out(pl, out4, dst, (size_t)n * 4, 0);
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_best_state(sb_plan* pl, float** snr_dev, float** amp_dev, int32_t** idx_dev) {
+    if (!pl) return fail("null plan");
+    if (snr_dev) *snr_dev = pl->d_bsnr;
+    if (amp_dev) *amp_dev = pl->d_bamp;
+    if (idx_dev) *idx_dev = pl->d_bidx;
+    return 0;
+}
+
+int sb_compare_host(sb_plan* pl, double* best4_host, const double* amp, const double* age, const double* angle,
+                    const double* snr, double age_s, double angle_s) {
+    if (!pl || !best4_host || !amp || !snr) return fail("sb_compare_host: null");
+    const long n = (long)pl->ny * pl->nx;
+    SB_OK(ensure(pl->raw, (size_t)n * 8 * sizeof(double)));
+    double* d = (double*)pl->raw.p;
+    SB_TRY(sb_rt_h2d(d, best4_host, (size_t)n * 4 * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_h2d(d + 4 * n, amp, (size_t)n * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_h2d(d + 5 * n, snr, (size_t)n * sizeof(double), pl->stream));
+    const double* d_age = nullptr;
+    const double* d_ang = nullptr;
+    if (age) { SB_TRY(sb_rt_h2d(d + 6 * n, age, (size_t)n * sizeof(double), pl->stream)); d_age = d + 6 * n; }
+    if (angle) { SB_TRY(sb_rt_h2d(d + 7 * n, angle, (size_t)n * sizeof(double), pl->stream)); d_ang = d + 7 * n; }
+    SB_LAUNCH(sb::k_compare, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, d, d + n, d + 2 * n, d + 3 * n,
+              (const double*)(d + 4 * n), d_age, d_ang, (const double*)(d + 5 * n), age_s, angle_s);
+    SB_OK(check_launch(pl, "k_compare"));
+    return copy_out(pl, best4_host, d, (size_t)n * 4, 0);
+}
+
+int sb_debug_fft(sb_plan* pl, int n, int rows, const float* in_host, float* out_host, int inverse) {
+    if (!pl || !in_host || !out_host || rows <= 0) return fail("sb_debug_fft: bad arguments");
+    const float2* tw = nullptr;
+    if (!is_pow2(n) || n < kMinFft || n > kMaxFftSupported) return fail("sb_debug_fft: unsupported length");
+    SB_OK(twiddles(pl, n, &tw));
+    const size_t bytes = (size_t)rows * n * sizeof(float2);
+    SB_OK(ensure(pl->raw, 2 * bytes));
+    float2* d_in = (float2*)pl->raw.p;
+    float2* d_out = d_in + (size_t)rows * n;
+    SB_TRY(sb_rt_h2d(d_in, in_host, bytes, pl->stream));
+    SB_OK(dispatch_n(n, [&](auto nn) {
+        constexpr int N = decltype(nn)::value;
+        using S = Shape<N>;
+        SB_ALLOW_SMEM(sb::k_fft_rows<N>, S::smem);
+        SB_LAUNCH(sb::k_fft_rows<N>, dim3(div_up(rows, S::GP)), dim3(S::threads), S::smem, pl->stream, rows,
+                  (const float2*)d_in, d_out, inverse, tw);
+        return check_launch(pl, "k_fft_rows");
+    }));
+    SB_TRY(sb_rt_d2h(out_host, d_out, bytes, pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+int sb_sync(sb_plan* pl) {
+    if (!pl) return fail("null plan");
+    SB_TRY(sb_rt_sync(pl->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Thin device-runtime layer used by every kernel in this library.
+//
+// Product build (nvcc, sm_100a): the macros below are the CUDA built-ins.
+// Test build (-DSB_EMU, g++): the same kernel source is compiled against
+// tests/emu/sb_emu.h, a fiber-per-CUDA-thread emulator, so that index logic can
+// be checked on a machine without a GPU.  The emulator is test infrastructure:
+// the product package never loads it (scarplet_b200/_lib.py only opens the
+// CUDA library and raises if it is missing).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+#ifdef SB_EMU
+#include "sb_emu.h"
+#else
+#include <cuda_runtime.h>
+
+#define SB_GLOBAL __global__ void
+#define SB_DEVICE __device__ __forceinline__
+#define SB_HOSTDEV __host__ __device__ __forceinline__
+#define SB_CONSTEXPR __host__ __device__ constexpr
+#define SB_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+#define SB_RESTRICT __restrict__
+
+SB_DEVICE int sb_tid() { return threadIdx.x; }
+SB_DEVICE int sb_bx() { return blockIdx.x; }
+SB_DEVICE int sb_by() { return blockIdx.y; }
+SB_DEVICE int sb_bz() { return blockIdx.z; }
+SB_DEVICE int sb_nbx() { return gridDim.x; }
+SB_DEVICE void sb_sync() { __syncthreads(); }
+SB_DEVICE void* sb_shared() {
+    extern __shared__ __align__(16) unsigned char sb_smem_raw[];
+    return sb_smem_raw;
+}
+template <typename T> SB_DEVICE T sb_ldg(const T* p) { return __ldg(p); }
+
+// IEEE operations that must not be contracted into FMAs (bit-exact float64
+// parity with NumPy for the curvature stencil and the template window).
+SB_DEVICE double sb_mul(double a, double b) { return __dmul_rn(a, b); }
+SB_DEVICE double sb_add(double a, double b) { return __dadd_rn(a, b); }
+SB_DEVICE double sb_sub(double a, double b) { return __dsub_rn(a, b); }
+SB_DEVICE double sb_div(double a, double b) { return __ddiv_rn(a, b); }
+
+typedef cudaStream_t sb_stream_t;
+
+#define SB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+
+inline int sb_rt_malloc(void** p, size_t n) { return (int)cudaMalloc(p, n); }
+inline int sb_rt_free(void* p) { return (int)cudaFree(p); }
+inline int sb_rt_h2d(void* d, const void* h, size_t n, sb_stream_t s) {
+    return (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s);
+}
+inline int sb_rt_d2h(void* h, const void* d, size_t n, sb_stream_t s) {
+    return (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s);
+}
+inline int sb_rt_d2d(void* d, const void* s0, size_t n, sb_stream_t s) {
+    return (int)cudaMemcpyAsync(d, s0, n, cudaMemcpyDeviceToDevice, s);
+}
+inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t s) {
+    return (int)cudaMemsetAsync(d, v, n, s);
+}
+inline int sb_rt_sync(sb_stream_t s) { return (int)cudaStreamSynchronize(s); }
+inline int sb_rt_last_error() { return (int)cudaGetLastError(); }
+inline const char* sb_rt_error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
+#endif

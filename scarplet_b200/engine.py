@@ -1,0 +1,196 @@
+"""Python handle on an ``sb_plan`` (include/scarplet_b200.h): owns the device
+workspace for one raster shape and drives sweeps.  Thin by design — tiling, batching
+and every kernel launch live in the CUDA library."""
+import ctypes
+from ctypes import byref, c_int, c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import SbAngle, SbTemplate, check
+from . import params as P
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Plan(object):
+    """One raster geometry bound to one CUDA device."""
+
+    def __init__(self, ny, nx, dx, dy, device=-1, stream=None, workspace_mb=None,
+                 max_fft=None, force_pad=None):
+        self.lib = _lib.load()
+        self.ny, self.nx = int(ny), int(nx)
+        self.dx, self.dy = dx, dy
+        self._h = c_void_p()
+        # dx ** 2 / dy ** 2 evaluated in Python like dem.py:95,99
+        check(self.lib, self.lib.sb_plan_create(byref(self._h), self.ny, self.nx, float(dx),
+                                                float(dx ** 2), float(dy ** 2), int(device),
+                                                c_void_p(stream or 0), 0))
+        self.x, self.y = P.axis_vectors(self.nx, self.ny, dx)     # de = dx, core.py:343
+        xs, ys = _as_f64(self.x), _as_f64(self.y)
+        check(self.lib, self.lib.sb_set_axes_host(self._h, xs.ctypes.data, ys.ctypes.data))
+        if workspace_mb is not None:
+            self.set_option("workspace_mb", workspace_mb)
+        if max_fft is not None:
+            self.set_option("max_fft", max_fft)
+        if force_pad is not None:
+            self.set_option("force_pad", int(force_pad))
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.sb_plan_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key, value):
+        check(self.lib, self.lib.sb_plan_set_option(self._h, key.encode(), int(value)))
+
+    @property
+    def launches(self):
+        return int(self.lib.sb_plan_launch_count(self._h))
+
+    def last_geometry(self):
+        out = (c_int * 6)()
+        check(self.lib, self.lib.sb_plan_last_geometry(self._h, out))
+        keys = ("Py", "Px", "tiles_y", "tiles_x", "angle_batch", "template_batch")
+        return dict(zip(keys, list(out)))
+
+    def sync(self):
+        check(self.lib, self.lib.sb_sync(self._h))
+
+    # -- inputs --------------------------------------------------------------
+    def set_dem(self, z):
+        """Upload ``DEMGrid._griddata`` (host float64, never modified)."""
+        z = _as_f64(z)
+        if z.shape != (self.ny, self.nx):
+            raise ValueError("DEM shape %r does not match the plan %r" % (z.shape, (self.ny, self.nx)))
+        check(self.lib, self.lib.sb_set_dem_host(self._h, z.ctypes.data))
+
+    def set_dem_device(self, ptr):
+        """Borrow a float64 device buffer (e.g. ``tensor.data_ptr()``)."""
+        check(self.lib, self.lib.sb_set_dem_dev(self._h, c_void_p(int(ptr))))
+
+    # -- single operations -----------------------------------------------------
+    def directional_laplacian(self, alpha):
+        out = np.empty((self.ny, self.nx), dtype=np.float64)
+        a = P.angle_record(alpha)
+        check(self.lib, self.lib.sb_directional_laplacian(self._h, byref(a), out.ctypes.data, 0))
+        return out
+
+    def render_template(self, spec, scale, age, angle):
+        rec = P.template_record(spec, scale, age, angle, self.nx, self.ny, self.dx,
+                                self.x, self.y, 0, 0)
+        out = np.empty((self.ny, self.nx), dtype=np.float64)
+        check(self.lib, self.lib.sb_render_template(self._h, byref(rec), out.ctypes.data, 0))
+        return out
+
+    def match_template(self, spec, scale, age, angle):
+        rec = P.template_record(spec, scale, age, angle, self.nx, self.ny, self.dx,
+                                self.x, self.y, 0, 0)
+        a = P.angle_record(angle)
+        amp = np.empty((self.ny, self.nx), dtype=np.float64)
+        snr = np.empty((self.ny, self.nx), dtype=np.float64)
+        check(self.lib, self.lib.sb_match_template(self._h, byref(a), byref(rec),
+                                                   amp.ctypes.data, snr.ctypes.data, 0))
+        return amp, snr
+
+    # -- sweeps ------------------------------------------------------------------
+    def build_sweep(self, spec, scale, ages, angles, order="age_major", angle_slice=None):
+        """Records for the fan-out over ``angles`` x ``ages``.
+
+        ``order`` fixes the flat result index (the tie priority of ``compare``):
+        ``"age_major"`` = ``match``'s hierarchical reduce (core.py:285-292),
+        ``"angle_major"`` = ``calculate_best_fit_parameters_serial`` (core.py:116-134).
+        ``angle_slice`` restricts the records to a contiguous shard of the angle list
+        (multi-GPU) without changing any index.
+        Returns ``(angle_records, template_records, age_of, angle_of)``.
+        """
+        ages = np.atleast_1d(np.asarray(ages, dtype=np.float64))
+        angles = np.asarray(angles, dtype=np.float64)
+        A, G = len(angles), len(ages)
+        lo, hi = (0, A) if angle_slice is None else angle_slice
+        arr_a = (SbAngle * max(hi - lo, 1))()
+        arr_t = (SbTemplate * max((hi - lo) * G, 1))()
+        age_of = np.empty(A * G, dtype=np.float64)
+        angle_of = np.empty(A * G, dtype=np.float64)
+        for ai in range(A):
+            for gi in range(G):
+                idx = gi * A + ai if order == "age_major" else ai * G + gi
+                age_of[idx] = ages[gi]
+                angle_of[idx] = angles[ai]
+        n = 0
+        for k, ai in enumerate(range(lo, hi)):
+            ang = angles[ai]
+            arr_a[k] = P.angle_record(ang)
+            for gi in range(G):
+                idx = gi * A + ai if order == "age_major" else ai * G + gi
+                arr_t[n] = P.template_record(spec, scale, ages[gi], ang, self.nx, self.ny,
+                                             self.dx, self.x, self.y, k, idx)
+                n += 1
+        return (arr_a, hi - lo), (arr_t, n), age_of, angle_of
+
+    def reset(self):
+        check(self.lib, self.lib.sb_best_reset(self._h))
+
+    def sweep(self, angle_records, template_records):
+        arr_a, na = angle_records
+        arr_t, nt = template_records
+        if nt == 0:
+            return
+        check(self.lib, self.lib.sb_sweep(self._h, arr_a, na, arr_t, nt))
+
+    def finalize(self, age_of, angle_of):
+        """(4, ny, nx) float64 stack [amp, age, angle, snr] (core.py:190-193)."""
+        age_of, angle_of = _as_f64(age_of), _as_f64(angle_of)
+        out = np.empty((4, self.ny, self.nx), dtype=np.float64)
+        check(self.lib, self.lib.sb_finalize(self._h, age_of.ctypes.data, angle_of.ctypes.data,
+                                             len(age_of), out.ctypes.data, 0))
+        return out
+
+    def best_state_pointers(self):
+        s, a, i = c_void_p(), c_void_p(), c_void_p()
+        check(self.lib, self.lib.sb_best_state(self._h, byref(s), byref(a), byref(i)))
+        return s.value, a.value, i.value
+
+    def compare_fold(self, best4, amp, age, angle, snr):
+        """One step of core.compare (core.py:230-240) with the reference's exact
+        strict-compare semantics, on the device in float64."""
+        amp, snr = _as_f64(amp), _as_f64(snr)
+        age_p = angle_p = None
+        age_s = angle_s = 0.0
+        if np.ndim(age) == 2:
+            age_p = _as_f64(age)
+        else:
+            age_s = float(age)
+        if np.ndim(angle) == 2:
+            angle_p = _as_f64(angle)
+        else:
+            angle_s = float(angle)
+        check(self.lib, self.lib.sb_compare_host(
+            self._h, best4.ctypes.data, amp.ctypes.data,
+            age_p.ctypes.data if age_p is not None else None,
+            angle_p.ctypes.data if angle_p is not None else None,
+            snr.ctypes.data, age_s, angle_s))
+        return best4
+
+    def debug_fft(self, x, inverse=False):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        rows, n = x.shape
+        out = np.empty_like(x)
+        check(self.lib, self.lib.sb_debug_fft(self._h, n, rows, x.ctypes.data, out.ctypes.data,
+                                              int(bool(inverse))))
+        return out

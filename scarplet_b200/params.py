@@ -1,0 +1,134 @@
+"""Host-side float64 precomputation for the device kernels.
+
+Everything that decides a mask or an index is evaluated here with NumPy exactly as
+the reference evaluates it (same expressions, same operation order), then handed to
+the CUDA library as plain numbers, so that masks come out bit-exact:
+
+* axis vectors ``x``, ``y``                     WindowedTemplate.py:50-53
+* ``cos``/``sin`` of the search angle and of ``alpha = -angle``   dem.py:103, WindowedTemplate.py:57
+* the edge mask of ``get_window_limits`` reduced to an index rectangle   WindowedTemplate.py:66-84
+* a conservative support box of the template (the device evaluates the exact window
+  ``(abs(xr) < c) & (abs(yr) < d)`` inside it)   WindowedTemplate.py:61-64
+"""
+import numpy as np
+from scipy.special import erfinv
+
+from ._lib import SbAngle, SbTemplate
+
+KIND_SCARP = 0
+KIND_RICKER = 1
+ERRMASK_NONE = 0
+ERRMASK_XR_LE0 = 1
+ERRMASK_XR_GE0 = 2
+
+# exp(-u**2) is exactly 0.0 in float64 beyond this u**2 (denormal underflow); it
+# bounds the Ricker support along xr (WindowedTemplate.py:514-515)
+_EXP_UNDERFLOW = 745.2
+
+
+def axis_vectors(nx, ny, de):
+    """Centred pixel coordinates, WindowedTemplate.py:50-53."""
+    x = de * np.linspace(1, nx, num=nx)
+    y = de * np.linspace(1, ny, num=ny)
+    x = x - np.mean(x)
+    y = y - np.mean(y)
+    return x, y
+
+
+def search_angles(ang_min, ang_max):
+    """1-degree orientation grid, core.py:173-175."""
+    ang_stepsize = 1
+    num_angles = int((180 / np.pi) * (ang_max - ang_min) / ang_stepsize + 1)
+    return np.linspace(ang_min, ang_max, num_angles)
+
+
+def default_ages():
+    """core.py:107, 286"""
+    return 10 ** np.arange(0, 3.5, 0.1)
+
+
+def angle_record(angle):
+    """Curvature direction as dem.py:103-104 evaluates it."""
+    return SbAngle(float(np.cos(angle)), float(np.sin(angle)),
+                   float(np.cos(angle) ** 2), float(np.sin(angle) ** 2))
+
+
+def scarp_halfwidth(kt):
+    """WindowedTemplate.py:156-157"""
+    frac = 0.9
+    return abs(2 * np.sqrt(kt) * erfinv(frac))
+
+
+def window_rectangle(x, y, alpha, c, d):
+    """Rows/cols NOT masked by ``get_window_limits`` (WindowedTemplate.py:66-84) as an
+    inclusive index rectangle ``(i_lo, i_hi, j_lo, j_hi)``; empty -> lo > hi."""
+    x4 = d * np.cos(alpha - np.pi / 2)
+    y4 = d * np.sin(alpha - np.pi / 2)
+    x1 = d * np.cos(alpha)
+    y1 = d * np.sin(alpha)
+    an_y = abs((x4 - x1) + 2 * c * np.cos(alpha - np.pi / 2))
+    an_x = abs((y1 - y4) + 2 * c * np.sin(alpha - np.pi / 2))
+    keep_x = ~((x < (min(x) + an_x)) | (x > (max(x) - an_x)))
+    keep_y = ~((y < (min(y) + an_y)) | (y > (max(y) - an_y)))
+    jj = np.flatnonzero(keep_x)
+    ii = np.flatnonzero(keep_y)
+    if jj.size == 0 or ii.size == 0:
+        return 1, 0, 1, 0
+    # x and y are monotonic, so the kept set is one run
+    return int(ii[0]), int(ii[-1]), int(jj[0]), int(jj[-1])
+
+
+def support_box(nx, ny, de, ca, sa, c_eff, d):
+    """Conservative bounding box of ``(abs(xr) < c_eff) & (abs(yr) < d)`` in pixel
+    offsets from the template centre ``(ny // 2, nx // 2)``, clipped to the raster."""
+    step = abs(float(de))
+    ex = (c_eff * abs(ca) + d * abs(sa)) / step
+    ey = (c_eff * abs(sa) + d * abs(ca)) / step
+    a0, b0 = ny // 2, nx // 2
+    rx = int(min(ex, 4.0 * nx)) + 2
+    ry = int(min(ey, 4.0 * ny)) + 2
+    sx_lo, sx_hi = max(-rx, -b0), min(rx, nx - 1 - b0)
+    sy_lo, sy_hi = max(-ry, -a0), min(ry, ny - 1 - a0)
+    return sy_lo, sy_hi, sx_lo, sx_hi
+
+
+class DeviceSpec(object):
+    """What a built-in template class contributes to an ``SbTemplate`` record."""
+
+    def __init__(self, kind, sign=1.0, errmode=ERRMASK_NONE, edge_mask=True):
+        self.kind = kind
+        self.sign = sign
+        self.errmode = errmode
+        self.edge_mask = edge_mask
+
+
+def template_record(spec, scale, age, angle, nx, ny, de, x, y, angle_id, idx):
+    """``SbTemplate`` for ``Template(scale, age, angle, nx, ny, de)`` (core.py:345)."""
+    alpha = -angle                                   # WindowedTemplate.py:151, 489
+    ca = float(np.cos(alpha))
+    sa = float(np.sin(alpha))
+    d = float(scale)
+    if spec.kind == KIND_SCARP:
+        kt = age
+        c = float(scarp_halfwidth(kt))
+        k0 = float(2. * kt ** (3 / 2.) * np.sqrt(np.pi))   # WindowedTemplate.py:177
+        k1 = float(4. * kt)                                # :178
+        c_eff = c
+    elif spec.kind == KIND_RICKER:
+        f = age
+        c = float(nx)                                      # WindowedTemplate.py:491
+        k0 = float(np.pi * f)                              # :514
+        k1 = 0.0
+        c_eff = c
+        if abs(k0) > 0:
+            c_eff = min(c, np.sqrt(_EXP_UNDERFLOW) / abs(k0) + abs(de))
+    else:
+        raise ValueError("unknown template kind %r" % (spec.kind,))
+    sy_lo, sy_hi, sx_lo, sx_hi = support_box(nx, ny, de, ca, sa, c_eff, d)
+    if spec.edge_mask:
+        i_lo, i_hi, j_lo, j_hi = window_rectangle(x, y, alpha, c, d)
+    else:
+        i_lo, i_hi, j_lo, j_hi = 0, ny - 1, 0, nx - 1      # WindowedTemplate.py:494-495
+    return SbTemplate(ca, sa, c, d, k0, k1, float(spec.sign), spec.kind, spec.errmode,
+                      sy_lo, sy_hi, sx_lo, sx_hi, i_lo, i_hi, j_lo, j_hi,
+                      int(angle_id), int(idx))

@@ -1,0 +1,173 @@
+// CPU emulator for the CUDA kernels of scarplet_b200 — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the unmodified kernel source (scarplet_b200/csrc/*.cuh, *.cu) with
+// g++ -DSB_EMU so the index logic of every kernel (FFT exchanges, Hermitian
+// unpacking, tile/halo bookkeeping, masks, argmax) can be exercised on a host
+// without a GPU.  Each CUDA thread of a block is a ucontext fiber; a block
+// barrier is a yield to the block scheduler; blocks are spread over OS threads.
+// Nothing here is product code: scarplet_b200/_lib.py never opens the emulator
+// library, and the parity claims are made by the `-m gpu` tests on a B200.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) {
+    float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r;
+}
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+namespace sbemu {
+
+struct Fiber {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    int tid = 0;
+    bool done = false;
+};
+
+struct Block {
+    int bx = 0, by = 0, bz = 0;
+    dim3 grid;
+    void* smem = nullptr;
+    ucontext_t sched;
+    Fiber* cur = nullptr;
+    const std::function<void()>* fn = nullptr;
+};
+
+inline Block*& current() {
+    static thread_local Block* b = nullptr;
+    return b;
+}
+
+inline void fiber_entry() {
+    Block* b = current();
+    (*b->fn)();
+    b->cur->done = true;
+    swapcontext(&b->cur->ctx, &b->sched);
+}
+
+constexpr size_t kStack = 256 * 1024;
+
+inline void run_blocks(dim3 grid, int nthreads, size_t smem_bytes,
+                       const std::function<void()>& fn, std::atomic<long>& next) {
+    std::vector<Fiber> fibers(nthreads);
+    for (auto& f : fibers) f.stack = (char*)std::malloc(kStack);
+    void* smem = nullptr;
+    if (posix_memalign(&smem, 128, smem_bytes + 128) != 0) std::abort();
+    Block blk;
+    blk.grid = grid;
+    blk.smem = smem;
+    blk.fn = &fn;
+    current() = &blk;
+    const long total = (long)grid.x * grid.y * grid.z;
+    for (;;) {
+        long b = next.fetch_add(1);
+        if (b >= total) break;
+        blk.bx = (int)(b % grid.x);
+        blk.by = (int)((b / grid.x) % grid.y);
+        blk.bz = (int)(b / ((long)grid.x * grid.y));
+        std::memset(smem, 0xCD, smem_bytes);  // poison: shared memory is uninitialised
+        for (int t = 0; t < nthreads; ++t) {
+            Fiber& f = fibers[t];
+            f.tid = t;
+            f.done = false;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = kStack;
+            f.ctx.uc_link = nullptr;
+            makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+        }
+        int alive = nthreads;
+        while (alive > 0) {
+            alive = 0;
+            for (int t = 0; t < nthreads; ++t) {
+                Fiber& f = fibers[t];
+                if (f.done) continue;
+                blk.cur = &f;
+                swapcontext(&blk.sched, &f.ctx);  // runs to the next barrier or to the end
+                if (!f.done) ++alive;
+            }
+        }
+    }
+    current() = nullptr;
+    std::free(smem);
+    for (auto& f : fibers) std::free(f.stack);
+}
+
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& fn) {
+    const long total = (long)grid.x * grid.y * grid.z;
+    if (total <= 0) return;
+    int nthreads = (int)(block.x * block.y * block.z);
+    int workers = (int)std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("SB_EMU_WORKERS")) workers = std::atoi(e);
+    workers = (int)std::max<long>(1, std::min<long>(workers, total));
+    std::atomic<long> next(0);
+    if (workers == 1) {
+        run_blocks(grid, nthreads, smem_bytes, fn, next);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int w = 0; w < workers; ++w)
+        pool.emplace_back([&] { run_blocks(grid, nthreads, smem_bytes, fn, next); });
+    for (auto& t : pool) t.join();
+}
+
+}  // namespace sbemu
+
+#define SB_GLOBAL static void
+#define SB_DEVICE inline
+#define SB_HOSTDEV inline
+#define SB_CONSTEXPR constexpr
+#define SB_LAUNCH_BOUNDS(t, b)
+#define SB_RESTRICT __restrict__
+
+SB_DEVICE int sb_tid() { return sbemu::current()->cur->tid; }
+SB_DEVICE int sb_bx() { return sbemu::current()->bx; }
+SB_DEVICE int sb_by() { return sbemu::current()->by; }
+SB_DEVICE int sb_bz() { return sbemu::current()->bz; }
+SB_DEVICE int sb_nbx() { return (int)sbemu::current()->grid.x; }
+SB_DEVICE void sb_sync() {
+    sbemu::Block* b = sbemu::current();
+    swapcontext(&b->cur->ctx, &b->sched);
+}
+SB_DEVICE void* sb_shared() { return sbemu::current()->smem; }
+template <typename T> SB_DEVICE T sb_ldg(const T* p) { return *p; }
+
+// built with -ffp-contract=off, so these stay separate IEEE operations
+SB_DEVICE double sb_mul(double a, double b) { return a * b; }
+SB_DEVICE double sb_add(double a, double b) { return a + b; }
+SB_DEVICE double sb_sub(double a, double b) { return a - b; }
+SB_DEVICE double sb_div(double a, double b) { return a / b; }
+
+typedef void* sb_stream_t;
+
+#define SB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    sbemu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+
+inline int sb_rt_malloc(void** p, size_t n) { return posix_memalign(p, 256, n ? n : 256) == 0 ? 0 : 2; }
+inline int sb_rt_free(void* p) { std::free(p); return 0; }
+inline int sb_rt_h2d(void* d, const void* h, size_t n, sb_stream_t) { std::memcpy(d, h, n); return 0; }
+inline int sb_rt_d2h(void* h, const void* d, size_t n, sb_stream_t) { std::memcpy(h, d, n); return 0; }
+inline int sb_rt_d2d(void* d, const void* s, size_t n, sb_stream_t) { std::memcpy(d, s, n); return 0; }
+inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t) { std::memset(d, v, n); return 0; }
+inline int sb_rt_sync(sb_stream_t) { return 0; }
+inline int sb_rt_last_error() { return 0; }
+inline const char* sb_rt_error_string(int) { return "emulator"; }

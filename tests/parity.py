@@ -1,0 +1,43 @@
+"""Shared parity metrics (north_star tolerances)."""
+import numpy as np
+
+AMP_SNR_RTOL = 1e-4        # north_star: amplitude and SNR relative error <= 1e-4
+INDEX_AGREEMENT = 0.999    # north_star: best angle/age identical on >= 99.9 % of valid pixels
+
+
+def stack_report(res, ref, odd_template=True):
+    """Compare two [amp, age, angle, snr] stacks.
+
+    Index agreement is counted modulo the +-90 degree degeneracy (the first and last
+    orientation are the same line; for odd templates the amplitude flips sign), as the
+    reference itself resolves that pair by 1e-11-level noise."""
+    res = np.asarray(res)
+    ref = np.asarray(ref)
+    amp, age, ang, snr = res
+    ramp, rage, rang, rsnr = ref
+    valid = rsnr > 0
+    nvalid = int(valid.sum())
+    same = (ang == rang) & (age == rage)
+    a_lo, a_hi = rang[valid].min() if nvalid else 0, rang[valid].max() if nvalid else 0
+    degenerate = np.zeros_like(valid)
+    if nvalid and np.isclose(a_hi - a_lo, np.pi):
+        degenerate = ((np.isclose(ang, a_lo) & np.isclose(rang, a_hi)) |
+                      (np.isclose(ang, a_hi) & np.isclose(rang, a_lo))) & (age == rage)
+    agree = (same | degenerate) & valid
+    sign = np.where(degenerate & odd_template, -1.0, 1.0)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        snr_rel = np.abs(snr - rsnr) / np.abs(rsnr)
+        amp_rel = np.abs(sign * amp - ramp) / np.abs(ramp)
+    return {
+        "valid": nvalid,
+        "mask_equal": bool(((snr > 0) == valid).all()),
+        "mask_mismatch": int(((snr > 0) != valid).sum()),
+        "index_agreement": float(agree.sum() / max(nvalid, 1)),
+        "snr_rel_max": float(snr_rel[agree].max()) if agree.any() else 0.0,
+        "snr_rel_p50": float(np.median(snr_rel[agree])) if agree.any() else 0.0,
+        "amp_rel_p999": float(np.quantile(amp_rel[agree], 0.999)) if agree.any() else 0.0,
+        "amp_rel_max": float(amp_rel[agree].max()) if agree.any() else 0.0,
+        "frac_snr_over_tol": float((snr_rel[agree] > AMP_SNR_RTOL).mean()) if agree.any() else 0.0,
+        "frac_amp_over_tol": float((amp_rel[agree] > AMP_SNR_RTOL).mean()) if agree.any() else 0.0,
+        "disagree_snr_gap_max": float(snr_rel[valid & ~agree].max()) if (valid & ~agree).any() else 0.0,
+    }
