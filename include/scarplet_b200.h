@@ -47,6 +47,7 @@ typedef struct sb_template {
     double c, d;          /* window half-widths (WindowedTemplate.py:63)                     */
     double k0, k1;        /* scarp: 2*kt**1.5*sqrt(pi), 4*kt;  ricker: pi*f, 0               */
     double sign;          /* -1 for RightFacingUpperBreakScarp (WindowedTemplate.py:254)    */
+    double tscale;        /* power of two ~ 1/rms(t): balances t against M in the packed FFT  */
     int32_t kind;         /* SB_KIND_*                                                       */
     int32_t errmode;      /* SB_ERRMASK_* (WindowedTemplate.py:257-267, 294-304)             */
     int32_t sy_lo, sy_hi, sx_lo, sx_hi; /* conservative support box, offsets from (ny//2, nx//2) */
@@ -69,8 +70,12 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
                    int device, void* stream, unsigned flags);
 int sb_plan_destroy(sb_plan* plan);
 
-/* tuning knobs: key in {"workspace_mb", "max_fft", "force_pad"}; returns 0 if known */
+/* tuning knobs: key in {"workspace_mb", "max_fft", "force_pad", "profile"}; returns 0 if known */
 int sb_plan_set_option(sb_plan* plan, const char* key, long value);
+/* per-kernel device time (CUDA events on the plan's stream) accumulated while the option
+ * "profile" is 1: ms[6], launches[6] in the order k_curv_rows, k_curv_cols, k_tmpl_rows,
+ * k_tmpl_sums, k_conv_cols, k_fit_rows.  reset != 0 clears the counters afterwards. */
+int sb_plan_profile(sb_plan* plan, double* ms6, long* launches6, int reset);
 /* number of kernels launched by this plan so far */
 long sb_plan_launch_count(const sb_plan* plan);
 /* FFT domain and tile grid chosen by the last sweep: out[0..5] = Py, Px, tiles_y, tiles_x, angle batch, template batch */
@@ -109,6 +114,16 @@ int sb_finalize(sb_plan* plan, const double* age_of_host, const double* angle_of
 
 /* Raw best state for a cross-GPU merge: device pointers into the plan, ny*nx each. */
 int sb_best_state(sb_plan* plan, float** snr_dev, float** amp_dev, int32_t** idx_dev);
+
+/* Cross-GPU merge of best states (the parent-side reduce over Pool results,
+ * core.py:185, when the search is sharded over ranks).  All buffers are device memory
+ * of ny*nx elements owned by the caller (e.g. torch tensors handed to NCCL):
+ *   1. sb_best_pack    keys = (SNR bits << 32) | (0xFFFFFFFF - idx)  -> all-reduce MAX (int64)
+ *   2. sb_best_select  amp_out = amp where this rank owns the winning key, else 0 -> all-reduce SUM
+ *   3. sb_best_unpack  overwrite the plan's best state with the merged result */
+int sb_best_pack(sb_plan* plan, unsigned long long* keys_dev);
+int sb_best_select(sb_plan* plan, const unsigned long long* gkeys_dev, float* amp_out_dev);
+int sb_best_unpack(sb_plan* plan, const unsigned long long* gkeys_dev, const float* amp_dev);
 
 /* core.compare (core.py:198-243) with the reference's exact strict-compare semantics on
  * float64 host planes: folds (amp, age, angle, snr) into best[4][n].  age/angle may be

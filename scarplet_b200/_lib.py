@@ -22,6 +22,7 @@ class SbTemplate(Structure):
     _fields_ = [("cos_t", c_double), ("sin_t", c_double),
                 ("c", c_double), ("d", c_double),
                 ("k0", c_double), ("k1", c_double), ("sign", c_double),
+                ("tscale", c_double),
                 ("kind", c_int32), ("errmode", c_int32),
                 ("sy_lo", c_int32), ("sy_hi", c_int32),
                 ("sx_lo", c_int32), ("sx_hi", c_int32),
@@ -49,6 +50,7 @@ def _declare(lib):
     lib.sb_plan_launch_count.argtypes = [P]
     lib.sb_plan_launch_count.restype = c_long
     lib.sb_plan_last_geometry.argtypes = [P, POINTER(c_int)]
+    lib.sb_plan_profile.argtypes = [P, POINTER(c_double), POINTER(c_long), c_int]
     lib.sb_set_dem_host.argtypes = [P, c_void_p]
     lib.sb_set_dem_dev.argtypes = [P, c_void_p]
     lib.sb_set_axes_host.argtypes = [P, c_void_p, c_void_p]
@@ -60,24 +62,29 @@ def _declare(lib):
     lib.sb_sweep.argtypes = [P, POINTER(SbAngle), c_int, POINTER(SbTemplate), c_int]
     lib.sb_finalize.argtypes = [P, c_void_p, c_void_p, c_int, c_void_p, c_int]
     lib.sb_best_state.argtypes = [P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
+    lib.sb_best_pack.argtypes = [P, c_void_p]
+    lib.sb_best_select.argtypes = [P, c_void_p, c_void_p]
+    lib.sb_best_unpack.argtypes = [P, c_void_p, c_void_p]
     lib.sb_compare_host.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_double, c_double]
     lib.sb_debug_fft.argtypes = [P, c_int, c_int, c_void_p, c_void_p, c_int]
     lib.sb_sync.argtypes = [P]
     for name in ("sb_plan_create", "sb_plan_destroy", "sb_plan_set_option",
-                 "sb_plan_last_geometry", "sb_set_dem_host", "sb_set_dem_dev",
+                 "sb_plan_last_geometry", "sb_plan_profile", "sb_set_dem_host", "sb_set_dem_dev",
                  "sb_set_axes_host", "sb_directional_laplacian", "sb_render_template",
                  "sb_match_template", "sb_best_reset", "sb_sweep", "sb_finalize",
-                 "sb_best_state", "sb_compare_host", "sb_debug_fft", "sb_sync"):
+                 "sb_best_state", "sb_best_pack", "sb_best_select", "sb_best_unpack",
+                 "sb_compare_host", "sb_debug_fft", "sb_sync"):
         getattr(lib, name).restype = c_int
     return lib
 
 
 EXPORTED = ("sb_last_error", "sb_build_info", "sb_plan_create", "sb_plan_destroy",
-            "sb_plan_set_option", "sb_plan_launch_count", "sb_plan_last_geometry",
+            "sb_plan_set_option", "sb_plan_launch_count", "sb_plan_last_geometry", "sb_plan_profile",
             "sb_set_dem_host", "sb_set_dem_dev", "sb_set_axes_host",
             "sb_directional_laplacian", "sb_render_template", "sb_match_template",
-            "sb_best_reset", "sb_sweep", "sb_finalize", "sb_best_state", "sb_compare_host",
+            "sb_best_reset", "sb_sweep", "sb_finalize", "sb_best_state", "sb_best_pack",
+            "sb_best_select", "sb_best_unpack", "sb_compare_host",
             "sb_debug_fft", "sb_sync")
 
 

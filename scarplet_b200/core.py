@@ -80,7 +80,10 @@ def match(data, Template, **kwargs):
     scale = kwargs['scale']
     ang_max = kwargs.get('ang_max', np.pi / 2)
     ang_min = kwargs.get('ang_min', -np.pi / 2)
-    out = _sweep(data, Template, scale, P.default_ages(), ang_max, ang_min, "age_major")
+    # extension: ``ages=`` replaces the hard-coded 35-age grid of core.py:286
+    ages = kwargs.get('ages', None)
+    ages = P.default_ages() if ages is None else np.asarray(ages, dtype=np.float64)
+    out = _sweep(data, Template, scale, ages, ang_max, ang_min, "age_major")
     return out[0], out[1], out[2], out[3]
 
 

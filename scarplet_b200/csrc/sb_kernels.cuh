@@ -38,6 +38,7 @@ struct Geom {
     int syp;                 // pitch (rows) of the per-template support block
     double dx, dx2, dy2;     // cell size, dx**2, dy**2 as the host computes them
     double norm;             // 1 / (Px * Py)
+    double c2_scale;         // power of two: curv**2 is packed as curv**2 * c2_scale next to curv
 };
 
 struct Angle {               // one search orientation (curvature direction)
@@ -49,6 +50,7 @@ struct Tmpl {                // one (scale, age, angle) template
     double c, d;             // half-widths of the curvature window
     double k0, k1;           // scarp: 2*kt**1.5*sqrt(pi), 4*kt   ricker: pi*f, unused
     double sign;             // -1 for the right-facing upper-break template
+    double tscale;           // power of two: t is packed as t * tscale next to M (0/1)
     int kind;                // 0 scarp family, 1 ricker/channel
     int errmode;             // 0 none, 1 snr=0 where xr<=0, 2 snr=0 where xr>=0
     int sy_lo, sy_hi, sx_lo, sx_hi;   // support box, offsets from (ny//2, nx//2)
@@ -184,7 +186,7 @@ k_curv_rows(Geom g, const double* SB_RESTRICT dem, const Angle* SB_RESTRICT angl
         if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
             const int gj = wrap(g.ox + sx, g.nx);
             const double c = curvature_at(dem, g.ny, g.nx, gi, gj, g.dx, g.dx2, g.dy2, ang);
-            val = make_float2((float)c, (float)(c * c));          // curv, curv**2 (core.py:355)
+            val = make_float2((float)c, (float)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
         }
         v[q] = val;
     }
@@ -267,7 +269,7 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
             if (w != 0.0) {                                   // M = template != 0, core.py:348
                 cnt += 1.0;
                 ssq += w * w;
-                val = make_float2((float)w, 1.f);
+                val = make_float2((float)(w * p.tscale), 1.f);
             }
         }
         v[q] = val;
@@ -424,6 +426,7 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
         const Tmpl p = tmpls[tmpl_base + pl];
         if (!raw && (cta_hi < p.i_lo || cta_lo > p.i_hi)) continue;   // whole CTA edge-masked
         const TSum s = sums[pl];
+        const double xc_norm = g.norm / p.tscale, t3_norm = g.norm / g.c2_scale;
         const float2* gt = gbuf + ((long)pl * 2 + 0) * g.out_ny * g.kpitch + (long)(active ? io : 0) * g.kpitch;
         const float2* gm = gt + (long)g.out_ny * g.kpitch;
         float2 v[E];
@@ -443,8 +446,8 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             if (gj[q] < 0) continue;
-            const double xc = (double)v[q].y * g.norm;           // Re ifft: xcorr   core.py:359
-            const double t3 = (double)v[q].x * g.norm;           // Im ifft: T3      core.py:363
+            const double xc = (double)v[q].y * xc_norm;          // Re ifft: xcorr   core.py:359
+            const double t3 = (double)v[q].x * t3_norm;          // Im ifft: T3      core.py:363
             double amp = xc * s.inv_ts;                          // core.py:360
             const double t1 = s.ts * amp * amp;                  // core.py:362
             const double err = s.inv_n * (t1 - 2.0 * amp * xc + t3) + kEps;   // core.py:366
@@ -493,6 +496,47 @@ SB_GLOBAL k_best_init(long n, float* snr, float* amp, int* idx) {
     if (i < n) { snr[i] = 0.f; amp[i] = 0.f; idx[i] = 0x7fffffff; }
 }
 
+// Cross-GPU merge of best states (replaces the parent-side compare over Pool results,
+// core.py:185): key = SNR bits (SNR >= 0, so IEEE order == integer order) in the high
+// word, inverted flat index in the low word -> integer max picks the highest SNR and,
+// on equal SNR, the lowest index.
+SB_GLOBAL k_best_pack(long n, const float* SB_RESTRICT snr, const int* SB_RESTRICT idx,
+                      unsigned long long* SB_RESTRICT keys) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    unsigned int bits;
+    const float s = snr[i];
+    memcpy(&bits, &s, 4);
+    keys[i] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
+}
+
+SB_GLOBAL k_best_select(long n, const float* SB_RESTRICT snr, const float* SB_RESTRICT amp,
+                        const int* SB_RESTRICT idx, const unsigned long long* SB_RESTRICT gkeys,
+                        float* SB_RESTRICT amp_out) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    unsigned int bits;
+    const float s = snr[i];
+    memcpy(&bits, &s, 4);
+    const unsigned long long own =
+        ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
+    amp_out[i] = (own == gkeys[i] && idx[i] != 0x7fffffff) ? amp[i] : 0.f;
+}
+
+SB_GLOBAL k_best_unpack(long n, const unsigned long long* SB_RESTRICT gkeys,
+                        const float* SB_RESTRICT amp_in, float* SB_RESTRICT snr, float* SB_RESTRICT amp,
+                        int* SB_RESTRICT idx) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    const unsigned long long k = gkeys[i];
+    const unsigned int bits = (unsigned int)(k >> 32);
+    float s;
+    memcpy(&s, &bits, 4);
+    snr[i] = s;
+    idx[i] = (int)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
+    amp[i] = amp_in[i];
+}
+
 // decode the best state into the reference's [amp, age, angle, snr] float64 planes
 SB_GLOBAL k_finalize(long n, const float* SB_RESTRICT snr, const float* SB_RESTRICT amp,
                      const int* SB_RESTRICT idx, const double* SB_RESTRICT age_of,
@@ -506,6 +550,31 @@ SB_GLOBAL k_finalize(long n, const float* SB_RESTRICT snr, const float* SB_RESTR
     out4[n + i] = hit ? age_of[k] : 0.0;
     out4[2 * n + i] = hit ? angle_of[k] : 0.0;
     out4[3 * n + i] = hit ? (double)s : 0.0;
+}
+
+// sum over the raster of dxx**2 + dyy**2 (per-block partials, fixed order): gives the
+// curvature scale used to balance curv against curv**2 in the packed FFT
+SB_GLOBAL k_curv_sumsq(int ny, int nx, const double* SB_RESTRICT dem, double dx, double dx2, double dy2,
+                       double* SB_RESTRICT partial) {
+    double* sd = (double*)sb_shared();
+    const long n = (long)ny * nx;
+    Angle a0, a1;
+    a0.ca = 1.0; a0.sa = 0.0; a0.ca2 = 1.0; a0.sa2 = 0.0;
+    a1.ca = 0.0; a1.sa = 1.0; a1.ca2 = 0.0; a1.sa2 = 1.0;
+    double acc = 0.0;
+    for (long i = (long)sb_bx() * 256 + sb_tid(); i < n; i += (long)sb_nbx() * 256) {
+        const int r = (int)(i / nx), c = (int)(i % nx);
+        const double u = curvature_at(dem, ny, nx, r, c, dx, dx2, dy2, a0);
+        const double v = curvature_at(dem, ny, nx, r, c, dx, dx2, dy2, a1);
+        acc += u * u + v * v;
+    }
+    sd[sb_tid()] = acc;
+    sb_sync();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (sb_tid() < w) sd[sb_tid()] += sd[sb_tid() + w];
+        sb_sync();
+    }
+    if (sb_tid() == 0) partial[sb_bx()] = sd[0];
 }
 
 // full-raster directional Laplacian in float64 (DEMGrid._calculate_directional_laplacian)

@@ -15,6 +15,7 @@ static_assert(sizeof(sb_angle) == sizeof(sb::Angle), "sb_angle / sb::Angle layou
 static_assert(offsetof(sb_template, kind) == offsetof(sb::Tmpl, kind), "layout");
 static_assert(offsetof(sb_template, idx) == offsetof(sb::Tmpl, idx), "layout");
 static_assert(offsetof(sb_template, i_lo) == offsetof(sb::Tmpl, i_lo), "layout");
+static_assert(offsetof(sb_template, tscale) == offsetof(sb::Tmpl, tscale), "layout");
 
 namespace {
 
@@ -79,6 +80,14 @@ struct sb_plan {
     std::map<int, float2*> tw;
     Buf cr, fct, trt, part, gbuf, sums, tmpls, angles, tables, raw;
     long launches = 0;
+    double c2_scale = 1.0;
+    int profile = 0;
+    std::vector<sb_event_t> ev_pool;
+    struct EvPair { int kind; sb_event_t a, b; };
+    std::vector<EvPair> ev_live;
+    size_t ev_used = 0;
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+    long prof_n[6] = {0, 0, 0, 0, 0, 0};
     long workspace_mb = 8192;
     int max_fft = kMaxFftSupported;
     int force_pad = 0;
@@ -171,6 +180,63 @@ int check_launch(sb_plan* pl, const char* what) {
 }
 
 int div_up(long a, long b) { return (int)((a + b - 1) / b); }
+
+enum { K_CURV_ROWS = 0, K_CURV_COLS, K_TMPL_ROWS, K_TMPL_SUMS, K_CONV_COLS, K_FIT_ROWS };
+
+sb_event_t take_event(sb_plan* pl) {
+    if (pl->ev_used == pl->ev_pool.size()) {
+        sb_event_t e;
+        sb_rt_event_create(&e);
+        pl->ev_pool.push_back(e);
+    }
+    return pl->ev_pool[pl->ev_used++];
+}
+
+struct ProfScope {   // brackets one launch with events when profiling is on
+    sb_plan* pl;
+    int kind;
+    sb_event_t a{}, b{};
+    ProfScope(sb_plan* p, int k) : pl(p), kind(k) {
+        if (pl->profile) { a = take_event(pl); sb_rt_event_record(a, pl->stream); }
+    }
+    ~ProfScope() {
+        if (pl->profile) {
+            b = take_event(pl);
+            sb_rt_event_record(b, pl->stream);
+            pl->ev_live.push_back({kind, a, b});
+        }
+    }
+};
+
+void drain_profile(sb_plan* pl) {
+    if (pl->ev_live.empty()) return;
+    sb_rt_sync(pl->stream);
+    for (auto& e : pl->ev_live) {
+        pl->prof_ms[e.kind] += sb_rt_event_ms(e.a, e.b);
+        pl->prof_n[e.kind]++;
+    }
+    pl->ev_live.clear();
+    pl->ev_used = 0;
+}
+
+// curvature RMS -> power-of-two factor that brings curv**2 to the magnitude of curv
+int update_curv_scale(sb_plan* pl) {
+    const int blocks = std::max(1, std::min(1024, div_up((long)pl->ny * pl->nx, 256)));
+    SB_OK(ensure(pl->raw, (size_t)blocks * sizeof(double)));
+    SB_LAUNCH(sb::k_curv_sumsq, dim3(blocks), dim3(256), 256 * sizeof(double), pl->stream, pl->ny, pl->nx,
+              (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, (double*)pl->raw.p);
+    SB_OK(check_launch(pl, "k_curv_sumsq"));
+    std::vector<double> part(blocks);
+    SB_TRY(sb_rt_d2h(part.data(), pl->raw.p, (size_t)blocks * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    double sum = 0.0;
+    for (double v : part) sum += v;
+    const double sigma = std::sqrt(sum / (2.0 * (double)pl->ny * (double)pl->nx));
+    pl->c2_scale = 1.0;
+    if (std::isfinite(sigma) && sigma > 1e-150 && sigma < 1e150)
+        pl->c2_scale = std::exp2(std::round(-std::log2(sigma)));
+    return 0;
+}
 
 // choose FFT length / tiling along one axis
 int plan_axis(const sb_plan* pl, int n, int lo, int hi, AxisPlan* ax) {
@@ -314,6 +380,7 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
             g.kpitch = kpitch; g.syp = syp;
             g.dx = pl->dx; g.dx2 = pl->dx2; g.dy2 = pl->dy2;
             g.norm = 1.0 / ((double)Px * (double)Py);
+            g.c2_scale = pl->c2_scale;
             const int need_rows = g.need_y_hi - g.need_y_lo + 1;
 
             for (int a0 = 0; a0 < n_angles; a0 += Ba) {
@@ -324,6 +391,7 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                     constexpr int N = decltype(nn)::value;
                     using S = Shape<N>;
                     SB_ALLOW_SMEM(sb::k_curv_rows<N>, S::smem);
+                    ProfScope prof(pl, K_CURV_ROWS);
                     SB_LAUNCH(sb::k_curv_rows<N>, dim3(div_up(need_rows, S::GP), a1 - a0), dim3(S::threads),
                               S::smem, pl->stream, g, (const double*)pl->d_dem, d_an, a0, (float4*)pl->cr.p, twx);
                     return check_launch(pl, "k_curv_rows");
@@ -332,6 +400,7 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                     constexpr int N = decltype(nn)::value;
                     using S = Shape<N>;
                     SB_ALLOW_SMEM(sb::k_curv_cols<N>, S::smem);
+                    ProfScope prof(pl, K_CURV_COLS);
                     SB_LAUNCH(sb::k_curv_cols<N>, dim3(div_up(KX, S::GP), a1 - a0), dim3(S::threads), S::smem,
                               pl->stream, g, (const float4*)pl->cr.p, (float2*)pl->fct.p, twy);
                     return check_launch(pl, "k_curv_cols");
@@ -342,18 +411,23 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N>;
                         SB_ALLOW_SMEM(sb::k_tmpl_rows<N>, S::smem);
+                        ProfScope prof(pl, K_TMPL_ROWS);
                         SB_LAUNCH(sb::k_tmpl_rows<N>, dim3(div_up(syp, S::GP), cnt), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
                                   (float4*)pl->trt.p, (double2*)pl->part.p, twx);
                         return check_launch(pl, "k_tmpl_rows");
                     }));
-                    SB_LAUNCH(sb::k_tmpl_sums, dim3(div_up(cnt, 32)), dim3(32), 0, pl->stream, g, d_tm, pb, cnt,
-                              (const double2*)pl->part.p, (sb::TSum*)pl->sums.p);
-                    SB_OK(check_launch(pl, "k_tmpl_sums"));
+                    {
+                        ProfScope prof(pl, K_TMPL_SUMS);
+                        SB_LAUNCH(sb::k_tmpl_sums, dim3(div_up(cnt, 32)), dim3(32), 0, pl->stream, g, d_tm, pb, cnt,
+                                  (const double2*)pl->part.p, (sb::TSum*)pl->sums.p);
+                        SB_OK(check_launch(pl, "k_tmpl_sums"));
+                    }
                     SB_OK(dispatch_n(Py, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N>;
                         SB_ALLOW_SMEM(sb::k_conv_cols<N>, S::smem);
+                        ProfScope prof(pl, K_CONV_COLS);
                         SB_LAUNCH(sb::k_conv_cols<N>, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
                                   (float2*)pl->gbuf.p, twy);
@@ -363,6 +437,7 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N>;
                         SB_ALLOW_SMEM(sb::k_fit_rows<N>, S::smem);
+                        ProfScope prof(pl, K_FIT_ROWS);
                         SB_LAUNCH(sb::k_fit_rows<N>, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, cnt, (const sb::TSum*)pl->sums.p,
                                   (const float2*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
@@ -371,6 +446,7 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                 }
             }
         }
+    drain_profile(pl);
     return 0;
 }
 
@@ -448,6 +524,7 @@ int sb_plan_destroy(sb_plan* pl) {
     if (pl->d_bamp) sb_rt_free(pl->d_bamp);
     if (pl->d_bidx) sb_rt_free(pl->d_bidx);
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
+    for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
     for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->tmpls, &pl->angles,
                    &pl->tables, &pl->raw})
         release(*b);
@@ -469,10 +546,22 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
         return 0;
     }
     if (k == "force_pad") { pl->force_pad = value != 0; return 0; }
+    if (k == "profile") { pl->profile = value != 0; return 0; }
     return fail("unknown option " + k);
 }
 
 long sb_plan_launch_count(const sb_plan* pl) { return pl ? pl->launches : 0; }
+
+int sb_plan_profile(sb_plan* pl, double* ms6, long* launches6, int reset) {
+    if (!pl) return fail("null plan");
+    drain_profile(pl);
+    for (int i = 0; i < 6; ++i) {
+        if (ms6) ms6[i] = pl->prof_ms[i];
+        if (launches6) launches6[i] = pl->prof_n[i];
+        if (reset) { pl->prof_ms[i] = 0; pl->prof_n[i] = 0; }
+    }
+    return 0;
+}
 
 int sb_plan_last_geometry(const sb_plan* pl, int* out6) {
     if (!pl || !out6) return fail("null");
@@ -490,7 +579,7 @@ int sb_set_dem_host(sb_plan* pl, const double* dem_host) {
     }
     SB_TRY(sb_rt_h2d(pl->d_dem, dem_host, bytes, pl->stream));
     SB_TRY(sb_rt_sync(pl->stream));
-    return 0;
+    return update_curv_scale(pl);
 }
 
 int sb_set_dem_dev(sb_plan* pl, const double* dem_dev) {
@@ -498,7 +587,7 @@ int sb_set_dem_dev(sb_plan* pl, const double* dem_dev) {
     if (pl->own_dem && pl->d_dem) sb_rt_free(pl->d_dem);
     pl->own_dem = false;
     pl->d_dem = const_cast<double*>(dem_dev);
-    return 0;
+    return update_curv_scale(pl);
 }
 
 int sb_set_axes_host(sb_plan* pl, const double* x_host, const double* y_host) {
@@ -614,6 +703,30 @@ int sb_best_state(sb_plan* pl, float** snr_dev, float** amp_dev, int32_t** idx_d
     if (amp_dev) *amp_dev = pl->d_bamp;
     if (idx_dev) *idx_dev = pl->d_bidx;
     return 0;
+}
+
+int sb_best_pack(sb_plan* pl, unsigned long long* keys_dev) {
+    if (!pl || !keys_dev) return fail("sb_best_pack: null");
+    const long n = (long)pl->ny * pl->nx;
+    SB_LAUNCH(sb::k_best_pack, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr,
+              (const int*)pl->d_bidx, keys_dev);
+    return check_launch(pl, "k_best_pack");
+}
+
+int sb_best_select(sb_plan* pl, const unsigned long long* gkeys_dev, float* amp_out_dev) {
+    if (!pl || !gkeys_dev || !amp_out_dev) return fail("sb_best_select: null");
+    const long n = (long)pl->ny * pl->nx;
+    SB_LAUNCH(sb::k_best_select, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr,
+              (const float*)pl->d_bamp, (const int*)pl->d_bidx, gkeys_dev, amp_out_dev);
+    return check_launch(pl, "k_best_select");
+}
+
+int sb_best_unpack(sb_plan* pl, const unsigned long long* gkeys_dev, const float* amp_dev) {
+    if (!pl || !gkeys_dev || !amp_dev) return fail("sb_best_unpack: null");
+    const long n = (long)pl->ny * pl->nx;
+    SB_LAUNCH(sb::k_best_unpack, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, gkeys_dev, amp_dev,
+              pl->d_bsnr, pl->d_bamp, pl->d_bidx);
+    return check_launch(pl, "k_best_unpack");
 }
 
 int sb_compare_host(sb_plan* pl, double* best4_host, const double* amp, const double* age, const double* angle,

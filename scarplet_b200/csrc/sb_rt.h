@@ -65,5 +65,10 @@ inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t s) {
 }
 inline int sb_rt_sync(sb_stream_t s) { return (int)cudaStreamSynchronize(s); }
 inline int sb_rt_last_error() { return (int)cudaGetLastError(); }
+typedef cudaEvent_t sb_event_t;
+inline int sb_rt_event_create(sb_event_t* e) { return (int)cudaEventCreate(e); }
+inline int sb_rt_event_destroy(sb_event_t e) { return (int)cudaEventDestroy(e); }
+inline int sb_rt_event_record(sb_event_t e, sb_stream_t s) { return (int)cudaEventRecord(e, s); }
+inline float sb_rt_event_ms(sb_event_t a, sb_event_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 inline const char* sb_rt_error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 #endif

@@ -63,6 +63,17 @@ class Plan(object):
     def launches(self):
         return int(self.lib.sb_plan_launch_count(self._h))
 
+    KERNELS = ("k_curv_rows", "k_curv_cols", "k_tmpl_rows", "k_tmpl_sums", "k_conv_cols",
+               "k_fit_rows")
+
+    def profile(self, reset=True):
+        """Per-kernel device time accumulated while option ``profile`` is on:
+        ``{kernel: (total_ms, launches)}``."""
+        ms = (ctypes.c_double * 6)()
+        n = (ctypes.c_long * 6)()
+        check(self.lib, self.lib.sb_plan_profile(self._h, ms, n, int(reset)))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNELS)}
+
     def last_geometry(self):
         out = (c_int * 6)()
         check(self.lib, self.lib.sb_plan_last_geometry(self._h, out))
@@ -165,6 +176,15 @@ class Plan(object):
         s, a, i = c_void_p(), c_void_p(), c_void_p()
         check(self.lib, self.lib.sb_best_state(self._h, byref(s), byref(a), byref(i)))
         return s.value, a.value, i.value
+
+    def best_pack(self, keys_ptr):
+        check(self.lib, self.lib.sb_best_pack(self._h, c_void_p(int(keys_ptr))))
+
+    def best_select(self, gkeys_ptr, amp_ptr):
+        check(self.lib, self.lib.sb_best_select(self._h, c_void_p(int(gkeys_ptr)), c_void_p(int(amp_ptr))))
+
+    def best_unpack(self, gkeys_ptr, amp_ptr):
+        check(self.lib, self.lib.sb_best_unpack(self._h, c_void_p(int(gkeys_ptr)), c_void_p(int(amp_ptr))))
 
     def compare_fold(self, best4, amp, age, angle, snr):
         """One step of core.compare (core.py:230-240) with the reference's exact

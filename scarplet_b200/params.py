@@ -92,6 +92,26 @@ def support_box(nx, ny, de, ca, sa, c_eff, d):
     return sy_lo, sy_hi, sx_lo, sx_hi
 
 
+def packing_scale(kind, k0, k1, half_width):
+    """Power of two close to 1 / rms(t) over the window.  The kernels transform the pair
+    (t * scale, M) as one complex row; without the factor the 0/1 mask M would dominate
+    the magnitude and its rounding noise would leak into the (much smaller) template
+    spectrum.  A power of two changes no mantissa bit, so results are unaffected
+    otherwise."""
+    if not np.isfinite(half_width) or half_width <= 0:
+        return 1.0
+    xr = (np.arange(256) + 0.5) / 256.0 * half_width
+    if kind == KIND_SCARP:
+        w = (xr / k0) * np.exp(-xr ** 2 / k1)
+    else:
+        u = k0 * xr
+        w = (1. - 2. * u ** 2) * np.exp(-u ** 2)
+    rms = float(np.sqrt(np.mean(w ** 2)))
+    if not np.isfinite(rms) or rms < 1e-280:
+        return 1.0
+    return float(2.0 ** np.clip(np.round(-np.log2(rms)), -300, 300))
+
+
 class DeviceSpec(object):
     """What a built-in template class contributes to an ``SbTemplate`` record."""
 
@@ -129,6 +149,7 @@ def template_record(spec, scale, age, angle, nx, ny, de, x, y, angle_id, idx):
         i_lo, i_hi, j_lo, j_hi = window_rectangle(x, y, alpha, c, d)
     else:
         i_lo, i_hi, j_lo, j_hi = 0, ny - 1, 0, nx - 1      # WindowedTemplate.py:494-495
-    return SbTemplate(ca, sa, c, d, k0, k1, float(spec.sign), spec.kind, spec.errmode,
+    tscale = packing_scale(spec.kind, k0, k1, c_eff)
+    return SbTemplate(ca, sa, c, d, k0, k1, float(spec.sign), tscale, spec.kind, spec.errmode,
                       sy_lo, sy_hi, sx_lo, sx_hi, i_lo, i_hi, j_lo, j_hi,
                       int(angle_id), int(idx))

@@ -170,4 +170,9 @@ inline int sb_rt_d2d(void* d, const void* s, size_t n, sb_stream_t) { std::memcp
 inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t) { std::memset(d, v, n); return 0; }
 inline int sb_rt_sync(sb_stream_t) { return 0; }
 inline int sb_rt_last_error() { return 0; }
+typedef int sb_event_t;
+inline int sb_rt_event_create(sb_event_t* e) { *e = 0; return 0; }
+inline int sb_rt_event_destroy(sb_event_t) { return 0; }
+inline int sb_rt_event_record(sb_event_t, sb_stream_t) { return 0; }
+inline float sb_rt_event_ms(sb_event_t, sb_event_t) { return 0.f; }
 inline const char* sb_rt_error_string(int) { return "emulator"; }
