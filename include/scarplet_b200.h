@@ -70,7 +70,8 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
                    int device, void* stream, unsigned flags);
 int sb_plan_destroy(sb_plan* plan);
 
-/* tuning knobs: key in {"workspace_mb", "max_fft", "force_pad", "profile"}; returns 0 if known */
+/* tuning knobs: key in {"workspace_mb", "max_fft", "force_pad", "profile",
+ * "precision" (32 = complex64 pipeline, default; 64 = complex128 pipeline)}; returns 0 if known */
 int sb_plan_set_option(sb_plan* plan, const char* key, long value);
 /* per-kernel device time (CUDA events on the plan's stream) accumulated while the option
  * "profile" is 1: ms[6], launches[6] in the order k_curv_rows, k_curv_cols, k_tmpl_rows,

@@ -1,4 +1,4 @@
-// Register-resident Stockham FFT for power-of-two lengths (complex64).
+// Register-resident Stockham FFT for power-of-two lengths, complex64 or complex128.
 //
 // One FFT of length N is carried by a group of T = N / E threads; thread t holds
 // E = 16 elements x[t + q*T], q = 0..E-1, in registers.  Every stage is a set of
@@ -38,7 +38,7 @@ SB_CONSTEXPR int stage_ns(int N, int s) {   // product of the radices before sta
     for (int i = 0; i < s; ++i) ns *= stage_radix(N, i);
     return ns;
 }
-// offset (in float2) of stage s in the twiddle table; stage 0 has no twiddles
+// offset (in elements) of stage s in the twiddle table; stage 0 has no twiddles
 SB_CONSTEXPR int twiddle_offset(int N, int s) {
     int off = 0;
     for (int i = 1; i < s; ++i) off += (stage_radix(N, i) - 1) * stage_ns(N, i);
@@ -46,8 +46,9 @@ SB_CONSTEXPR int twiddle_offset(int N, int s) {
 }
 SB_CONSTEXPR int twiddle_count(int N) { return twiddle_offset(N, num_stages(N)); }
 
-// host: fill the table for length N (float64 sincos rounded once to float32)
-inline void fill_twiddles(int N, float2* out) {
+// host: fill the table for length N (float64 sincos, rounded once for complex64)
+template <typename R>
+inline void fill_twiddles(int N, typename Vec<R>::v2* out) {
     int ns = 1, off = 0;
     for (int s = 0; N > ns; ++s) {
         int rest = N / ns;
@@ -56,7 +57,8 @@ inline void fill_twiddles(int N, float2* out) {
             for (int u = 1; u < r; ++u)
                 for (int k = 0; k < ns; ++k) {
                     double a = -2.0 * M_PI * (double)u * (double)k / ((double)ns * (double)r);
-                    out[off + (u - 1) * ns + k] = make_float2((float)cos(a), (float)sin(a));
+                    out[off + (u - 1) * ns + k].x = (R)cos(a);
+                    out[off + (u - 1) * ns + k].y = (R)sin(a);
                 }
             off += (r - 1) * ns;
         }
@@ -65,27 +67,29 @@ inline void fill_twiddles(int N, float2* out) {
 }
 
 // ---- small DFTs in registers ------------------------------------------------
-SB_DEVICE float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-SB_DEVICE float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-SB_DEVICE float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+template <typename C> SB_DEVICE C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> SB_DEVICE C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> SB_DEVICE C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }
-SB_DEVICE float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+template <typename C> SB_DEVICE C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }   // a * (-i)
 
-template <int R> struct Dft;
+template <typename R, int RADIX> struct Dft;
 
-template <> struct Dft<2> {
-    SB_DEVICE static void run(float2* x) {
-        float2 a = x[0], b = x[1];
+template <typename R> struct Dft<R, 2> {
+    typedef typename Vec<R>::v2 C;
+    SB_DEVICE static void run(C* x) {
+        C a = x[0], b = x[1];
         x[0] = cadd(a, b);
         x[1] = csub(a, b);
     }
 };
 
-template <> struct Dft<4> {
-    SB_DEVICE static void run(float2* x) {
-        float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
-        float2 t2 = cadd(x[1], x[3]), t3 = mul_mi(csub(x[1], x[3]));
+template <typename R> struct Dft<R, 4> {
+    typedef typename Vec<R>::v2 C;
+    SB_DEVICE static void run(C* x) {
+        C t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+        C t2 = cadd(x[1], x[3]), t3 = mul_mi(csub(x[1], x[3]));
         x[0] = cadd(t0, t2);
         x[2] = csub(t0, t2);
         x[1] = cadd(t1, t3);
@@ -93,17 +97,18 @@ template <> struct Dft<4> {
     }
 };
 
-template <> struct Dft<8> {
-    SB_DEVICE static void run(float2* x) {
-        const float h = 0.70710678118654752440f;
-        float2 e[4] = {x[0], x[2], x[4], x[6]};
-        float2 o[4] = {x[1], x[3], x[5], x[7]};
-        Dft<4>::run(e);
-        Dft<4>::run(o);
+template <typename R> struct Dft<R, 8> {
+    typedef typename Vec<R>::v2 C;
+    SB_DEVICE static void run(C* x) {
+        const R h = (R)0.70710678118654752440;
+        C e[4] = {x[0], x[2], x[4], x[6]};
+        C o[4] = {x[1], x[3], x[5], x[7]};
+        Dft<R, 4>::run(e);
+        Dft<R, 4>::run(o);
         // o[k] *= W8^k
-        o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+        o[1] = mk2<R>(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
         o[2] = mul_mi(o[2]);
-        o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+        o[3] = mk2<R>(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             x[k] = cadd(e[k], o[k]);
@@ -112,24 +117,25 @@ template <> struct Dft<8> {
     }
 };
 
-template <> struct Dft<16> {
-    SB_DEVICE static void run(float2* x) {
-        const float h = 0.70710678118654752440f;
-        const float c1 = 0.92387953251128675613f;   // cos(pi/8)
-        const float s1 = 0.38268343236508977173f;   // sin(pi/8)
-        float2 e[8], o[8];
+template <typename R> struct Dft<R, 16> {
+    typedef typename Vec<R>::v2 C;
+    SB_DEVICE static void run(C* x) {
+        const R h = (R)0.70710678118654752440;
+        const R c1 = (R)0.92387953251128675613;   // cos(pi/8)
+        const R s1 = (R)0.38268343236508977173;   // sin(pi/8)
+        C e[8], o[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
-        Dft<8>::run(e);
-        Dft<8>::run(o);
+        Dft<R, 8>::run(e);
+        Dft<R, 8>::run(o);
         // o[k] *= W16^k = exp(-i*pi*k/8)
-        o[1] = cmul(o[1], make_float2(c1, -s1));
-        o[2] = make_float2(h * (o[2].x + o[2].y), h * (o[2].y - o[2].x));
-        o[3] = cmul(o[3], make_float2(s1, -c1));
+        o[1] = cmul(o[1], mk2<R>(c1, -s1));
+        o[2] = mk2<R>(h * (o[2].x + o[2].y), h * (o[2].y - o[2].x));
+        o[3] = cmul(o[3], mk2<R>(s1, -c1));
         o[4] = mul_mi(o[4]);
-        o[5] = cmul(o[5], make_float2(-s1, -c1));
-        o[6] = make_float2(h * (o[6].y - o[6].x), -h * (o[6].x + o[6].y));
-        o[7] = cmul(o[7], make_float2(-c1, -s1));
+        o[5] = cmul(o[5], mk2<R>(-s1, -c1));
+        o[6] = mk2<R>(h * (o[6].y - o[6].x), -h * (o[6].x + o[6].y));
+        o[7] = cmul(o[7], mk2<R>(-c1, -s1));
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             x[k] = cadd(e[k], o[k]);
@@ -141,33 +147,35 @@ template <> struct Dft<16> {
 // ---- one Stockham stage ----------------------------------------------------
 // v[q] = x[t + q*T] on entry.  On exit the same layout holds the stage output
 // (after the exchange for all but the last stage).
-template <int N, int S>
-SB_DEVICE void stage(float2 (&v)[E], int t, float2* sm, const float2* SB_RESTRICT tw) {
+template <int N, int S, typename R>
+SB_DEVICE void stage(typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm,
+                     const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C;
     constexpr int T = N / E;
-    constexpr int R = stage_radix(N, S);
+    constexpr int RADIX = stage_radix(N, S);
     constexpr int NS = stage_ns(N, S);
-    constexpr int B = E / R;                 // butterflies per thread
-    constexpr bool LAST = (NS * R == N);
+    constexpr int B = E / RADIX;             // butterflies per thread
+    constexpr bool LAST = (NS * RADIX == N);
     constexpr int TWO = twiddle_offset(N, S);
 #pragma unroll
     for (int m = 0; m < B; ++m) {
-        const int j = t + m * T;             // butterfly index in [0, N/R)
-        float2 x[R];
+        const int j = t + m * T;             // butterfly index in [0, N/RADIX)
+        C x[RADIX];
 #pragma unroll
-        for (int u = 0; u < R; ++u) x[u] = v[m + u * B];
+        for (int u = 0; u < RADIX; ++u) x[u] = v[m + u * B];
         if (NS > 1) {
             const int k = j & (NS - 1);
 #pragma unroll
-            for (int u = 1; u < R; ++u) x[u] = cmul(x[u], sb_ldg(tw + TWO + (u - 1) * NS + k));
+            for (int u = 1; u < RADIX; ++u) x[u] = cmul(x[u], ld2(tw + TWO + (u - 1) * NS + k));
         }
-        Dft<R>::run(x);
+        Dft<R, RADIX>::run(x);
         if (LAST) {
 #pragma unroll
-            for (int u = 0; u < R; ++u) v[m + u * B] = x[u];
+            for (int u = 0; u < RADIX; ++u) v[m + u * B] = x[u];
         } else {
-            const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+            const int base = (j / NS) * (NS * RADIX) + (j & (NS - 1));
 #pragma unroll
-            for (int u = 0; u < R; ++u) sm[pad_index(base + u * NS)] = x[u];
+            for (int u = 0; u < RADIX; ++u) sm[pad_index(base + u * NS)] = x[u];
         }
     }
     if (!LAST) {
@@ -178,25 +186,22 @@ SB_DEVICE void stage(float2 (&v)[E], int t, float2* sm, const float2* SB_RESTRIC
     }
 }
 
-template <int N, int S = 0>
+template <int N, typename R, int S = 0>
 struct Stages {
-    SB_DEVICE static void run(float2 (&v)[E], int t, float2* sm, const float2* SB_RESTRICT tw) {
-        stage<N, S>(v, t, sm, tw);
-        if constexpr (S + 1 < num_stages(N)) Stages<N, S + 1>::run(v, t, sm, tw);
+    typedef typename Vec<R>::v2 C;
+    SB_DEVICE static void run(C (&v)[E], int t, C* sm, const C* SB_RESTRICT tw) {
+        stage<N, S, R>(v, t, sm, tw);
+        if constexpr (S + 1 < num_stages(N)) Stages<N, R, S + 1>::run(v, t, sm, tw);
     }
 };
 
 // Forward FFT of length N over the group's registers.  `sm` is the group's
-// private exchange buffer of padded_len(N) float2.  All threads of the CTA must
+// private exchange buffer of padded_len(N) elements.  All threads of the CTA must
 // call this together (it contains CTA-wide barriers).
-template <int N>
-SB_DEVICE void forward(float2 (&v)[E], int t, float2* sm, const float2* SB_RESTRICT tw) {
-    Stages<N, 0>::run(v, t, sm, tw);
-}
-
-SB_DEVICE void swap_all(float2 (&v)[E]) {
-#pragma unroll
-    for (int q = 0; q < E; ++q) v[q] = make_float2(v[q].y, v[q].x);
+template <int N, typename R>
+SB_DEVICE void forward(typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm,
+                       const typename Vec<R>::v2* SB_RESTRICT tw) {
+    Stages<N, R, 0>::run(v, t, sm, tw);
 }
 
 }  // namespace sbfft

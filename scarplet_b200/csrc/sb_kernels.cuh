@@ -136,10 +136,13 @@ SB_DEVICE double template_at(const Tmpl& p, double x, double y) {
 
 // Hermitian split of the spectrum Z of a packed pair a + i*b of real rows:
 // F[a](k) = (Z(k) + conj Z(-k)) / 2,  F[b](k) = (Z(k) - conj Z(-k)) / (2i).
-// v holds Z[t + q*T]; writes float4 (F[a], F[b]) for k = 0..N/2 to out[k * stride].
-template <int N>
-SB_DEVICE void hermitian_split(const float2 (&v)[E], int t, float2* sm, float4* out, long stride,
+// v holds Z[t + q*T]; writes C4 (F[a], F[b]) for k = 0..N/2 to out[k * stride].
+template <int N, typename R>
+SB_DEVICE void hermitian_split(const typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm,
+                               typename Vec<R>::v4* out, long stride,
                                bool active) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
 #pragma unroll
     for (int q = 0; q < E; ++q) sm[sbfft::pad_index(t + q * T)] = v[q];
@@ -147,15 +150,15 @@ SB_DEVICE void hermitian_split(const float2 (&v)[E], int t, float2* sm, float4* 
 #pragma unroll
     for (int q = 0; q < E / 2; ++q) {
         const int k = t + q * T;
-        const float2 zp = sm[sbfft::pad_index((N - k) & (N - 1))];
-        const float2 a = v[q];
+        const C2 zp = sm[sbfft::pad_index((N - k) & (N - 1))];
+        const C2 a = v[q];
         if (active)
-            out[(long)k * stride] = make_float4(0.5f * (a.x + zp.x), 0.5f * (a.y - zp.y),
-                                                0.5f * (a.y + zp.y), -0.5f * (a.x - zp.x));
+            out[(long)k * stride] = mk4<R>((R)0.5 * (a.x + zp.x), (R)0.5 * (a.y - zp.y),
+                                                (R)0.5 * (a.y + zp.y), -(R)0.5 * (a.x - zp.x));
     }
     if (t == 0 && active) {
-        const float2 a = v[E / 2];                 // Nyquist, index N/2 = (E/2)*T
-        out[(long)(N / 2) * stride] = make_float4(a.x, 0.f, a.y, 0.f);
+        const C2 a = v[E / 2];                 // Nyquist, index N/2 = (E/2)*T
+        out[(long)(N / 2) * stride] = mk4<R>(a.x, (R)0, a.y, (R)0);
     }
     sb_sync();
 }
@@ -163,73 +166,77 @@ SB_DEVICE void hermitian_split(const float2 (&v)[E], int t, float2* sm, float4* 
 // ---------------------------------------------------------------------------
 // k_curv_rows<Px>: grid (ceil(need_rows / GP), n_angles)
 // ---------------------------------------------------------------------------
-template <int N>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+template <int N, typename R>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_curv_rows(Geom g, const double* SB_RESTRICT dem, const Angle* SB_RESTRICT angles, int angle_base,
-            float4* SB_RESTRICT cr, const float2* SB_RESTRICT tw) {
+            typename Vec<R>::v4* SB_RESTRICT cr, const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int need_rows = g.need_y_hi - g.need_y_lo + 1;
     const int r = sb_bx() * GP + grp;
     const bool active = r < need_rows;
     const int a_loc = sb_by();
     const Angle ang = angles[angle_base + a_loc];
-    float2 v[E];
+    C2 v[E];
     const int gi = wrap(g.oy + g.need_y_lo + (active ? r : 0), g.ny);
 #pragma unroll
     for (int q = 0; q < E; ++q) {
         const int qx = t + q * T;
         const int sx = qx < g.split_x ? qx : qx - N;
-        float2 val = make_float2(0.f, 0.f);
+        C2 val = mk2<R>((R)0, (R)0);
         if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
             const int gj = wrap(g.ox + sx, g.nx);
             const double c = curvature_at(dem, g.ny, g.nx, gi, gj, g.dx, g.dx2, g.dy2, ang);
-            val = make_float2((float)c, (float)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
+            val = mk2<R>((R)c, (R)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
         }
         v[q] = val;
     }
-    sbfft::forward<N>(v, t, sm, tw);
-    float4* out = cr + ((long)a_loc * need_rows + (active ? r : 0)) * g.kpitch;
-    hermitian_split<N>(v, t, sm, out, 1, active);
+    sbfft::forward<N, R>(v, t, sm, tw);
+    C4* out = cr + ((long)a_loc * need_rows + (active ? r : 0)) * g.kpitch;
+    hermitian_split<N, R>(v, t, sm, out, 1, active);
 }
 
 // ---------------------------------------------------------------------------
 // k_curv_cols<Py>: grid (ceil(KX / GP), n_angles).  Column FFT of both fields.
-// fct layout: [angle][field][kx][Py] float2
+// fct layout: [angle][field][kx][Py] C2
 // ---------------------------------------------------------------------------
-template <int N>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
-k_curv_cols(Geom g, const float4* SB_RESTRICT cr, float2* SB_RESTRICT fct,
-            const float2* SB_RESTRICT tw) {
+template <int N, typename R>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
+k_curv_cols(Geom g, const typename Vec<R>::v4* SB_RESTRICT cr, typename Vec<R>::v2* SB_RESTRICT fct,
+            const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int KX = g.Px / 2 + 1;
     const int need_rows = g.need_y_hi - g.need_y_lo + 1;
     const int kx = sb_bx() * GP + grp;
     const bool active = kx < KX;
     const int a_loc = sb_by();
-    const float4* src = cr + (long)a_loc * need_rows * g.kpitch + (active ? kx : 0);
+    const C4* src = cr + (long)a_loc * need_rows * g.kpitch + (active ? kx : 0);
 #pragma unroll 1
     for (int f = 0; f < 2; ++f) {
-        float2 v[E];
+        C2 v[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int qy = t + q * T;
             const int sy = qy < g.split_y ? qy : qy - N;
-            float2 val = make_float2(0.f, 0.f);
+            C2 val = mk2<R>((R)0, (R)0);
             if (active && sy >= g.need_y_lo && sy <= g.need_y_hi) {
-                const float4 w = sb_ldg(src + (long)(sy - g.need_y_lo) * g.kpitch);
-                val = f == 0 ? make_float2(w.x, w.y) : make_float2(w.z, w.w);
+                const C4 w = ld4(src + (long)(sy - g.need_y_lo) * g.kpitch);
+                val = f == 0 ? mk2<R>(w.x, w.y) : mk2<R>(w.z, w.w);
             }
             v[q] = val;
         }
-        sbfft::forward<N>(v, t, sm, tw);
+        sbfft::forward<N, R>(v, t, sm, tw);
         if (active) {
-            float2* dst = fct + (((long)a_loc * 2 + f) * KX + kx) * N;
+            C2* dst = fct + (((long)a_loc * 2 + f) * KX + kx) * N;
 #pragma unroll
             for (int q = 0; q < E; ++q) dst[t + q * T] = v[q];
         }
@@ -238,17 +245,19 @@ k_curv_cols(Geom g, const float4* SB_RESTRICT cr, float2* SB_RESTRICT fct,
 
 // ---------------------------------------------------------------------------
 // k_tmpl_rows<Px>: grid (ceil(syp / GP), n_templates)
-// trt layout: [template][kx][syp] float4 (F_row[t], F_row[M]);  part: [template][syp] double2
+// trt layout: [template][kx][syp] C4 (F_row[t], F_row[M]);  part: [template][syp] double2
 // ---------------------------------------------------------------------------
-template <int N>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+template <int N, typename R>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* SB_RESTRICT xvec,
-            const double* SB_RESTRICT yvec, float4* SB_RESTRICT trt, double2* SB_RESTRICT part,
-            const float2* SB_RESTRICT tw) {
+            const double* SB_RESTRICT yvec, typename Vec<R>::v4* SB_RESTRICT trt, double2* SB_RESTRICT part,
+            const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int p_loc = sb_by();
     const Tmpl p = tmpls[tmpl_base + p_loc];
     const int rows = p.sy_hi - p.sy_lo + 1;
@@ -256,20 +265,20 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
     const bool active = r < rows;
     const int KX = N / 2 + 1;
     const int a0 = g.ny / 2, b0 = g.nx / 2;
-    float2 v[E];
+    C2 v[E];
     double cnt = 0.0, ssq = 0.0;
     const double y = active ? sb_ldg(yvec + a0 + p.sy_lo + r) : 0.0;
 #pragma unroll
     for (int q = 0; q < E; ++q) {
         const int qx = t + q * T;
         const int b = qx < N / 2 ? qx : qx - N;
-        float2 val = make_float2(0.f, 0.f);
+        C2 val = mk2<R>((R)0, (R)0);
         if (active && b >= p.sx_lo && b <= p.sx_hi) {
             const double w = template_at(p, sb_ldg(xvec + b0 + b), y);
             if (w != 0.0) {                                   // M = template != 0, core.py:348
                 cnt += 1.0;
                 ssq += w * w;
-                val = make_float2((float)(w * p.tscale), 1.f);
+                val = mk2<R>((R)(w * p.tscale), (R)1);
             }
         }
         v[q] = val;
@@ -292,9 +301,9 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
         }
         sb_sync();
     }
-    sbfft::forward<N>(v, t, sm, tw);
-    float4* out = trt + (long)p_loc * KX * g.syp + (active ? r : 0);
-    hermitian_split<N>(v, t, sm, out, g.syp, active);
+    sbfft::forward<N, R>(v, t, sm, tw);
+    C4* out = trt + (long)p_loc * KX * g.syp + (active ? r : 0);
+    hermitian_split<N, R>(v, t, sm, out, g.syp, active);
 }
 
 // one thread per template: fixed-order sum of the per-row partials
@@ -320,56 +329,58 @@ SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int 
 
 // ---------------------------------------------------------------------------
 // k_conv_cols<Py>: grid (ceil(KX / GP), n_templates)
-// gbuf layout: [template][field][out_ny][kpitch] float2
+// gbuf layout: [template][field][out_ny][kpitch] C2
 // ---------------------------------------------------------------------------
-template <int N>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+template <int N, typename R>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_conv_cols(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_base,
-            const float4* SB_RESTRICT trt, const float2* SB_RESTRICT fct, float2* SB_RESTRICT gbuf,
-            const float2* SB_RESTRICT tw) {
+            const typename Vec<R>::v4* SB_RESTRICT trt, const typename Vec<R>::v2* SB_RESTRICT fct, typename Vec<R>::v2* SB_RESTRICT gbuf,
+            const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int KX = g.Px / 2 + 1;
     const int kx = sb_bx() * GP + grp;
     const bool active = kx < KX;
     const int p_loc = sb_by();
     const Tmpl p = tmpls[tmpl_base + p_loc];
     const int a_loc = p.angle_id - angle_base;
-    const float4* src = trt + ((long)p_loc * KX + (active ? kx : 0)) * g.syp;
+    const C4* src = trt + ((long)p_loc * KX + (active ? kx : 0)) * g.syp;
 #pragma unroll 1
     for (int f = 0; f < 2; ++f) {
-        float2 v[E];
+        C2 v[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int qy = t + q * T;
             const int s = qy < N / 2 ? qy : qy - N;
-            float2 val = make_float2(0.f, 0.f);
+            C2 val = mk2<R>((R)0, (R)0);
             if (active && s >= p.sy_lo && s <= p.sy_hi) {
-                const float4 w = sb_ldg(src + (s - p.sy_lo));
-                val = f == 0 ? make_float2(w.x, w.y) : make_float2(w.z, w.w);
+                const C4 w = ld4(src + (s - p.sy_lo));
+                val = f == 0 ? mk2<R>(w.x, w.y) : mk2<R>(w.z, w.w);
             }
             v[q] = val;
         }
-        sbfft::forward<N>(v, t, sm, tw);
+        sbfft::forward<N, R>(v, t, sm, tw);
         {
-            const float2* spec = fct + (((long)a_loc * 2 + f) * KX + (active ? kx : 0)) * N;
+            const C2* spec = fct + (((long)a_loc * 2 + f) * KX + (active ? kx : 0)) * N;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
-                const float2 w = sb_ldg(spec + t + q * T);
-                const float2 pr = sbfft::cmul(v[q], w);           // core.py:359 / :363
-                v[q] = make_float2(pr.y, pr.x);                   // swap: inverse via forward
+                const C2 w = ld2(spec + t + q * T);
+                const C2 pr = sbfft::cmul(v[q], w);           // core.py:359 / :363
+                v[q] = mk2<R>(pr.y, pr.x);                   // swap: inverse via forward
             }
         }
-        sbfft::forward<N>(v, t, sm, tw);
+        sbfft::forward<N, R>(v, t, sm, tw);
         if (active) {
-            float2* dst = gbuf + ((long)p_loc * 2 + f) * g.out_ny * g.kpitch + kx;
+            C2* dst = gbuf + ((long)p_loc * 2 + f) * g.out_ny * g.kpitch + kx;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int m = t + q * T;
                 const int io = (m + g.dly) & (N - 1);
-                if (io < g.out_ny) dst[(long)io * g.kpitch] = make_float2(v[q].y, v[q].x);
+                if (io < g.out_ny) dst[(long)io * g.kpitch] = mk2<R>(v[q].y, v[q].x);
             }
         }
     }
@@ -386,16 +397,18 @@ struct FitOut {
     double* raw_snr;
 };
 
-template <int N>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+template <int N, typename R>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
-           const TSum* SB_RESTRICT sums, const float2* SB_RESTRICT gbuf,
+           const TSum* SB_RESTRICT sums, const typename Vec<R>::v2* SB_RESTRICT gbuf,
            const double* SB_RESTRICT xvec, const double* SB_RESTRICT yvec, FitOut out,
-           const float2* SB_RESTRICT tw) {
+           const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int io = sb_bx() * GP + grp;
     const bool active = io < g.out_ny;
     const int gi = g.oy + io;
@@ -427,22 +440,22 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
         if (!raw && (cta_hi < p.i_lo || cta_lo > p.i_hi)) continue;   // whole CTA edge-masked
         const TSum s = sums[pl];
         const double xc_norm = g.norm / p.tscale, t3_norm = g.norm / g.c2_scale;
-        const float2* gt = gbuf + ((long)pl * 2 + 0) * g.out_ny * g.kpitch + (long)(active ? io : 0) * g.kpitch;
-        const float2* gm = gt + (long)g.out_ny * g.kpitch;
-        float2 v[E];
+        const C2* gt = gbuf + ((long)pl * 2 + 0) * g.out_ny * g.kpitch + (long)(active ? io : 0) * g.kpitch;
+        const C2* gm = gt + (long)g.out_ny * g.kpitch;
+        C2 v[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int k = t + q * T;
             const bool direct = k <= N / 2;
             const int kk = direct ? k : N - k;
-            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-            if (active) { a = sb_ldg(gt + kk); b = sb_ldg(gm + kk); }
+            C2 a = mk2<R>((R)0, (R)0), b = mk2<R>((R)0, (R)0);
+            if (active) { a = ld2(gt + kk); b = ld2(gm + kk); }
             // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
-            const float2 x = direct ? make_float2(a.x - b.y, a.y + b.x)
-                                    : make_float2(a.x + b.y, b.x - a.y);
-            v[q] = make_float2(x.y, x.x);
+            const C2 x = direct ? mk2<R>(a.x - b.y, a.y + b.x)
+                                    : mk2<R>(a.x + b.y, b.x - a.y);
+            v[q] = mk2<R>(x.y, x.x);
         }
-        sbfft::forward<N>(v, t, sm, tw);
+        sbfft::forward<N, R>(v, t, sm, tw);
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             if (gj[q] < 0) continue;
@@ -618,26 +631,27 @@ SB_GLOBAL k_compare(long n, double* best_amp, double* best_age, double* best_ang
 }
 
 // debugging / unit-test kernel: batched forward FFT of length N, rows of `in`
-template <int N>
-SB_GLOBAL k_fft_rows(int rows, const float2* SB_RESTRICT in, float2* SB_RESTRICT outp, int inverse,
-                     const float2* SB_RESTRICT tw) {
+template <int N, typename R>
+SB_GLOBAL k_fft_rows(int rows, const typename Vec<R>::v2* SB_RESTRICT in, typename Vec<R>::v2* SB_RESTRICT outp, int inverse,
+                     const typename Vec<R>::v2* SB_RESTRICT tw) {
+    typedef typename Vec<R>::v2 C2;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    float2* sm = (float2*)sb_shared() + grp * sbfft::padded_len(N);
+    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int r = sb_bx() * GP + grp;
     const bool active = r < rows;
-    float2 v[E];
+    C2 v[E];
 #pragma unroll
     for (int q = 0; q < E; ++q) {
-        float2 a = active ? in[(long)r * N + t + q * T] : make_float2(0.f, 0.f);
-        v[q] = inverse ? make_float2(a.y, a.x) : a;
+        C2 a = active ? in[(long)r * N + t + q * T] : mk2<R>((R)0, (R)0);
+        v[q] = inverse ? mk2<R>(a.y, a.x) : a;
     }
-    sbfft::forward<N>(v, t, sm, tw);
+    sbfft::forward<N, R>(v, t, sm, tw);
     if (active) {
 #pragma unroll
         for (int q = 0; q < E; ++q)
-            outp[(long)r * N + t + q * T] = inverse ? make_float2(v[q].y, v[q].x) : v[q];
+            outp[(long)r * N + t + q * T] = inverse ? mk2<R>(v[q].y, v[q].x) : v[q];
     }
 }
 

@@ -77,7 +77,8 @@ struct sb_plan {
     float* d_bsnr = nullptr;
     float* d_bamp = nullptr;
     int* d_bidx = nullptr;
-    std::map<int, float2*> tw;
+    std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
+    int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
     Buf cr, fct, trt, part, gbuf, sums, tmpls, angles, tables, raw;
     long launches = 0;
     double c2_scale = 1.0;
@@ -112,10 +113,13 @@ void release(Buf& b) {
     b.cap = 0;
 }
 
-int twiddles(sb_plan* pl, int n, const float2** out) {
-    auto it = pl->tw.find(n);
+template <typename R>
+int twiddles(sb_plan* pl, int n, const typename Vec<R>::v2** out) {
+    typedef typename Vec<R>::v2 C2;
+    const long key = 2L * n + (sizeof(R) == 8 ? 1 : 0);
+    auto it = pl->tw.find(key);
     if (it != pl->tw.end()) {
-        *out = it->second;
+        *out = (const C2*)it->second;
         return 0;
     }
     int count = 0;
@@ -127,14 +131,14 @@ int twiddles(sb_plan* pl, int n, const float2** out) {
             ns *= r;
         }
     }
-    std::vector<float2> host(std::max(count, 1));
-    sbfft::fill_twiddles(n, host.data());
+    std::vector<C2> host(std::max(count, 1));
+    sbfft::fill_twiddles<R>(n, host.data());
     void* d = nullptr;
-    SB_TRY(sb_rt_malloc(&d, host.size() * sizeof(float2)));
-    SB_TRY(sb_rt_h2d(d, host.data(), host.size() * sizeof(float2), pl->stream));
+    SB_TRY(sb_rt_malloc(&d, host.size() * sizeof(C2)));
+    SB_TRY(sb_rt_h2d(d, host.data(), host.size() * sizeof(C2), pl->stream));
     SB_TRY(sb_rt_sync(pl->stream));
-    pl->tw[n] = (float2*)d;
-    *out = (float2*)d;
+    pl->tw[key] = d;
+    *out = (const C2*)d;
     return 0;
 }
 
@@ -152,12 +156,12 @@ int dispatch_n(int n, F&& f) {
     }
 }
 
-template <int N>
+template <int N, typename R>
 struct Shape {
     static constexpr int T = N / sbfft::E;
     static constexpr int threads = T > 256 ? T : 256;
     static constexpr int GP = threads / T;
-    static constexpr size_t smem = (size_t)GP * sbfft::padded_len(N) * sizeof(float2);
+    static constexpr size_t smem = (size_t)GP * sbfft::padded_len(N) * sizeof(typename Vec<R>::v2);
 };
 
 #ifndef SB_EMU
@@ -295,9 +299,13 @@ struct SweepOut {
     double* raw_snr = nullptr;
 };
 
-int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in,
-              int n_tmpls, SweepOut so) {
+template <typename R>
+int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in,
+                int n_tmpls, SweepOut so) {
+    typedef typename Vec<R>::v2 C2;
+    typedef typename Vec<R>::v4 C4;
     if (!pl->d_dem) return fail("no DEM set (sb_set_dem_host / sb_set_dem_dev)");
+    if (pl->ny < 3 || pl->nx < 3) return fail("raster too small for a template search");
     if (!pl->d_x || !pl->d_y) return fail("no axis vectors set (sb_set_axes_host)");
     if (n_tmpls <= 0 || n_angles <= 0) return 0;
 
@@ -325,14 +333,14 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
     const int KX = Px / 2 + 1;
     const int kpitch = Px / 2 + 8;
 
-    const float2 *twy = nullptr, *twx = nullptr;
-    SB_OK(twiddles(pl, Py, &twy));
-    SB_OK(twiddles(pl, Px, &twx));
+    const C2 *twy = nullptr, *twx = nullptr;
+    SB_OK(twiddles<R>(pl, Py, &twy));
+    SB_OK(twiddles<R>(pl, Px, &twx));
 
     // batch sizes from the workspace budget
     const int need_rows_max = ay.periodic ? Py : std::min(Py, ay.tile_out + (hi_y - lo_y) + 2);
-    const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(float4) + (size_t)2 * KX * Py * sizeof(float2);
-    const size_t per_tmpl = (size_t)KX * syp * sizeof(float4) + (size_t)2 * ay.tile_out * kpitch * sizeof(float2) +
+    const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
+    const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)2 * ay.tile_out * kpitch * sizeof(C2) +
                             (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
     const size_t budget = (size_t)pl->workspace_mb << 20;
     // templates per angle (max) decides the split of the budget
@@ -349,11 +357,11 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
     if (max_per_angle == 1) Bt = std::min(Bt, Ba), Ba = std::min(Ba, Bt);
     Bt = std::min(Bt, n_tmpls);
 
-    SB_OK(ensure(pl->cr, (size_t)Ba * need_rows_max * kpitch * sizeof(float4)));
-    SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(float2)));
-    SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(float4)));
+    SB_OK(ensure(pl->cr, (size_t)Ba * need_rows_max * kpitch * sizeof(C4)));
+    SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(C2)));
+    SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(C4)));
     SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
-    SB_OK(ensure(pl->gbuf, (size_t)Bt * 2 * ay.tile_out * kpitch * sizeof(float2)));
+    SB_OK(ensure(pl->gbuf, (size_t)Bt * 2 * ay.tile_out * kpitch * sizeof(C2)));
     SB_OK(ensure(pl->sums, (size_t)Bt * sizeof(sb::TSum)));
     SB_OK(ensure(pl->tmpls, (size_t)n_tmpls * sizeof(sb::Tmpl)));
     SB_OK(ensure(pl->angles, (size_t)n_angles * sizeof(sb::Angle)));
@@ -389,32 +397,35 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                 if (p1 == p0) continue;
                 SB_OK(dispatch_n(Px, [&](auto nn) {
                     constexpr int N = decltype(nn)::value;
-                    using S = Shape<N>;
-                    SB_ALLOW_SMEM(sb::k_curv_rows<N>, S::smem);
+                    using S = Shape<N, R>;
+                    auto kern = sb::k_curv_rows<N, R>;
+                    SB_ALLOW_SMEM(kern, S::smem);
                     ProfScope prof(pl, K_CURV_ROWS);
-                    SB_LAUNCH(sb::k_curv_rows<N>, dim3(div_up(need_rows, S::GP), a1 - a0), dim3(S::threads),
-                              S::smem, pl->stream, g, (const double*)pl->d_dem, d_an, a0, (float4*)pl->cr.p, twx);
+                    SB_LAUNCH(kern, dim3(div_up(need_rows, S::GP), a1 - a0), dim3(S::threads),
+                              S::smem, pl->stream, g, (const double*)pl->d_dem, d_an, a0, (C4*)pl->cr.p, twx);
                     return check_launch(pl, "k_curv_rows");
                 }));
                 SB_OK(dispatch_n(Py, [&](auto nn) {
                     constexpr int N = decltype(nn)::value;
-                    using S = Shape<N>;
-                    SB_ALLOW_SMEM(sb::k_curv_cols<N>, S::smem);
+                    using S = Shape<N, R>;
+                    auto kern = sb::k_curv_cols<N, R>;
+                    SB_ALLOW_SMEM(kern, S::smem);
                     ProfScope prof(pl, K_CURV_COLS);
-                    SB_LAUNCH(sb::k_curv_cols<N>, dim3(div_up(KX, S::GP), a1 - a0), dim3(S::threads), S::smem,
-                              pl->stream, g, (const float4*)pl->cr.p, (float2*)pl->fct.p, twy);
+                    SB_LAUNCH(kern, dim3(div_up(KX, S::GP), a1 - a0), dim3(S::threads), S::smem,
+                              pl->stream, g, (const C4*)pl->cr.p, (C2*)pl->fct.p, twy);
                     return check_launch(pl, "k_curv_cols");
                 }));
                 for (int pb = p0; pb < p1; pb += Bt) {
                     const int cnt = std::min(Bt, p1 - pb);
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
-                        using S = Shape<N>;
-                        SB_ALLOW_SMEM(sb::k_tmpl_rows<N>, S::smem);
+                        using S = Shape<N, R>;
+                        auto kern = sb::k_tmpl_rows<N, R>;
+                        SB_ALLOW_SMEM(kern, S::smem);
                         ProfScope prof(pl, K_TMPL_ROWS);
-                        SB_LAUNCH(sb::k_tmpl_rows<N>, dim3(div_up(syp, S::GP), cnt), dim3(S::threads), S::smem,
+                        SB_LAUNCH(kern, dim3(div_up(syp, S::GP), cnt), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
-                                  (float4*)pl->trt.p, (double2*)pl->part.p, twx);
+                                  (C4*)pl->trt.p, (double2*)pl->part.p, twx);
                         return check_launch(pl, "k_tmpl_rows");
                     }));
                     {
@@ -425,22 +436,24 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
                     }
                     SB_OK(dispatch_n(Py, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
-                        using S = Shape<N>;
-                        SB_ALLOW_SMEM(sb::k_conv_cols<N>, S::smem);
+                        using S = Shape<N, R>;
+                        auto kern = sb::k_conv_cols<N, R>;
+                        SB_ALLOW_SMEM(kern, S::smem);
                         ProfScope prof(pl, K_CONV_COLS);
-                        SB_LAUNCH(sb::k_conv_cols<N>, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem,
-                                  pl->stream, g, d_tm, pb, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
-                                  (float2*)pl->gbuf.p, twy);
+                        SB_LAUNCH(kern, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem,
+                                  pl->stream, g, d_tm, pb, a0, (const C4*)pl->trt.p, (const C2*)pl->fct.p,
+                                  (C2*)pl->gbuf.p, twy);
                         return check_launch(pl, "k_conv_cols");
                     }));
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
-                        using S = Shape<N>;
-                        SB_ALLOW_SMEM(sb::k_fit_rows<N>, S::smem);
+                        using S = Shape<N, R>;
+                        auto kern = sb::k_fit_rows<N, R>;
+                        SB_ALLOW_SMEM(kern, S::smem);
                         ProfScope prof(pl, K_FIT_ROWS);
-                        SB_LAUNCH(sb::k_fit_rows<N>, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
+                        SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, cnt, (const sb::TSum*)pl->sums.p,
-                                  (const float2*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
+                                  (const C2*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
                         return check_launch(pl, "k_fit_rows");
                     }));
                 }
@@ -448,6 +461,12 @@ int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templa
         }
     drain_profile(pl);
     return 0;
+}
+
+int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in, int n_tmpls,
+              SweepOut so) {
+    if (pl->precision == 64) return run_sweep_t<double>(pl, angles, n_angles, tmpls_in, n_tmpls, so);
+    return run_sweep_t<float>(pl, angles, n_angles, tmpls_in, n_tmpls, so);
 }
 
 int copy_out(sb_plan* pl, double* dst, const double* src_dev, size_t count, int out_is_device) {
@@ -476,7 +495,7 @@ const char* sb_build_info(void) {
 int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double dy2, int device,
                    void* stream, unsigned flags) {
     (void)flags;
-    if (!plan || ny < 3 || nx < 3) return fail("sb_plan_create: bad arguments");
+    if (!plan || ny < 1 || nx < 1) return fail("sb_plan_create: bad arguments");
     sb_plan* pl = new sb_plan();
     pl->ny = ny; pl->nx = nx; pl->dx = dx; pl->dx2 = dx2; pl->dy2 = dy2;
 #ifndef SB_EMU
@@ -547,6 +566,11 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
     }
     if (k == "force_pad") { pl->force_pad = value != 0; return 0; }
     if (k == "profile") { pl->profile = value != 0; return 0; }
+    if (k == "precision") {
+        if (value != 32 && value != 64) return fail("precision must be 32 or 64");
+        pl->precision = (int)value;
+        return 0;
+    }
     return fail("unknown option " + k);
 }
 
@@ -752,7 +776,7 @@ int sb_debug_fft(sb_plan* pl, int n, int rows, const float* in_host, float* out_
     if (!pl || !in_host || !out_host || rows <= 0) return fail("sb_debug_fft: bad arguments");
     const float2* tw = nullptr;
     if (!is_pow2(n) || n < kMinFft || n > kMaxFftSupported) return fail("sb_debug_fft: unsupported length");
-    SB_OK(twiddles(pl, n, &tw));
+    SB_OK(twiddles<float>(pl, n, &tw));
     const size_t bytes = (size_t)rows * n * sizeof(float2);
     SB_OK(ensure(pl->raw, 2 * bytes));
     float2* d_in = (float2*)pl->raw.p;
@@ -760,9 +784,10 @@ int sb_debug_fft(sb_plan* pl, int n, int rows, const float* in_host, float* out_
     SB_TRY(sb_rt_h2d(d_in, in_host, bytes, pl->stream));
     SB_OK(dispatch_n(n, [&](auto nn) {
         constexpr int N = decltype(nn)::value;
-        using S = Shape<N>;
-        SB_ALLOW_SMEM(sb::k_fft_rows<N>, S::smem);
-        SB_LAUNCH(sb::k_fft_rows<N>, dim3(div_up(rows, S::GP)), dim3(S::threads), S::smem, pl->stream, rows,
+        using S = Shape<N, float>;
+        auto kern = sb::k_fft_rows<N, float>;
+        SB_ALLOW_SMEM(kern, S::smem);
+        SB_LAUNCH(kern, dim3(div_up(rows, S::GP)), dim3(S::threads), S::smem, pl->stream, rows,
                   (const float2*)d_in, d_out, inverse, tw);
         return check_launch(pl, "k_fft_rows");
     }));

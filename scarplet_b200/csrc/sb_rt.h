@@ -72,3 +72,25 @@ inline int sb_rt_event_record(sb_event_t e, sb_stream_t s) { return (int)cudaEve
 inline float sb_rt_event_ms(sb_event_t a, sb_event_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 inline const char* sb_rt_error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 #endif
+
+// ---- precision-generic vector types ------------------------------------------
+template <typename R> struct Vec;
+template <> struct Vec<float> { typedef float2 v2; typedef float4 v4; };
+template <> struct Vec<double> { typedef double2 v2; typedef double4 v4; };
+
+template <typename R> SB_DEVICE typename Vec<R>::v2 mk2(R x, R y);
+template <> SB_DEVICE float2 mk2<float>(float x, float y) { return make_float2(x, y); }
+template <> SB_DEVICE double2 mk2<double>(double x, double y) { return make_double2(x, y); }
+template <typename R> SB_DEVICE typename Vec<R>::v4 mk4(R x, R y, R z, R w);
+template <> SB_DEVICE float4 mk4<float>(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+template <> SB_DEVICE double4 mk4<double>(double x, double y, double z, double w) { return make_double4(x, y, z, w); }
+
+// read-only loads of the vector types (double4 goes as two 16-byte loads)
+SB_DEVICE float2 ld2(const float2* p) { return sb_ldg(p); }
+SB_DEVICE double2 ld2(const double2* p) { return sb_ldg(p); }
+SB_DEVICE float4 ld4(const float4* p) { return sb_ldg(p); }
+SB_DEVICE double4 ld4(const double4* p) {
+    const double2 a = sb_ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = sb_ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}

@@ -49,6 +49,13 @@ def golden():
 @pytest.fixture(scope="session")
 def cuda_lib():
     """The product library on a CUDA device (gpu tests only)."""
+    if os.environ.get("SB_DEBUG_EMU") == "1":
+        # developer aid: run the parity tests against the CPU emulator build of the kernels
+        from tests.emu.build_emu import build
+        from scarplet_b200 import _lib
+        lib = _lib.open_library(build())
+        _lib._use_library(lib)
+        return lib
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

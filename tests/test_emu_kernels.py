@@ -1,0 +1,130 @@
+"""Index logic of the CUDA kernels, checked on CPU through the fiber emulator
+(tests/emu): the SAME kernel source compiled with g++ -DSB_EMU.  These tests do not
+establish GPU parity (tests/test_gpu_parity.py does, on a B200); they keep the FFT
+exchanges, Hermitian packing, halo/tile bookkeeping, masks and the best-state fold from
+regressing when no GPU is at hand."""
+import numpy as np
+import pytest
+
+from oracle import scarplet_oracle as O
+from tests.parity import stack_report
+
+
+def test_emulator_is_not_the_product(emu_lib):
+    assert emu_lib.sb_build_info() == b"cpu-emulator (test infrastructure)"
+
+
+@pytest.mark.parametrize("n", [128, 256, 1024, 4096, 8192])
+def test_fft_lengths(emu_lib, n):
+    from scarplet_b200.engine import Plan
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))).astype(np.complex64)
+    with Plan(8, 8, 1.0, 1.0) as plan:
+        y = plan.debug_fft(x)
+        yi = plan.debug_fft(x, inverse=True)
+    ref = np.fft.fft(x.astype(np.complex128), axis=1)
+    assert np.abs(y - ref).max() / np.abs(ref).max() < 5e-7
+    assert np.abs(yi - np.conj(np.fft.fft(np.conj(x.astype(np.complex128)), axis=1))).max() / np.abs(ref).max() < 5e-7
+
+
+def test_laplacian_bit_exact_and_nan(emu_lib):
+    import scarplet_b200 as sl
+    rng = np.random.default_rng(0)
+    z = (rng.standard_normal((37, 53)) * 10).astype(np.float32).astype(np.float64)
+    z[5, 6] = np.nan
+    for alpha in (0.0, -np.pi / 2, 0.77):
+        out = sl.DEMGrid(z, 2.0, 2.0)._calculate_directional_laplacian(alpha)
+        assert np.array_equal(out, O.directional_laplacian(z, 2.0, 2.0, alpha), equal_nan=True)
+
+
+def test_template_render_matches_oracle(emu_lib):
+    from scarplet_b200 import WindowedTemplate as WT
+    for angle in (0.0, 0.4, -np.pi / 2):
+        t = WT.Scarp(12, 4.0, angle, 61, 50, 1.0).template()
+        ref = O.template_array(O.SCARP, 12, 4.0, angle, 61, 50, 1.0)
+        assert np.array_equal(t != 0, ref != 0) and np.allclose(t, ref, rtol=1e-13, atol=0)
+        t = WT.Channel(5, 0.2, angle, 64, 47, 1.0).template()
+        ref = O.template_array(O.RICKER, 5, 0.2, angle, 64, 47, 1.0)
+        assert np.array_equal(t != 0, ref != 0) and np.allclose(t, ref, rtol=1e-12, atol=1e-300)
+        t = WT.RightFacingUpperBreakScarp(12, 4.0, angle, 61, 50, 1.0).template()
+        assert np.allclose(t, O.template_array(O.RIGHT_UPPER, 12, 4.0, angle, 61, 50, 1.0), rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("shape,cls,kind,scale,age,angle", [
+    ((128, 128), "Scarp", O.SCARP, 8, 2.0, 0.3),              # periodic domain
+    ((100, 150), "Scarp", O.SCARP, 8, 2.0, -1.1),             # padded, rectangular
+    ((61, 75), "Scarp", O.SCARP, 6, 4.0, np.pi / 2),          # odd sizes
+    ((64, 128), "Channel", O.RICKER, 5, 0.2, 0.7),            # wrap-around output is live
+    ((63, 90), "Channel", O.RICKER, 5, 0.02, -0.4),           # support clipped by the raster
+    ((80, 96), "LeftFacingUpperBreakScarp", O.LEFT_UPPER, 8, 3.0, 0.5),
+    ((80, 96), "RightFacingUpperBreakScarp", O.RIGHT_UPPER, 8, 3.0, -0.5),
+])
+@pytest.mark.parametrize("precision", [32, 64])
+def test_match_template_vs_oracle(emu_lib, shape, cls, kind, scale, age, angle, precision):
+    import scarplet_b200 as sl
+    from scarplet_b200 import WindowedTemplate as WT
+    from scarplet_b200.synth import synthetic_dem
+    z = synthetic_dem(shape[0], seed=shape[1], nx=shape[1], relief=3.0)
+    try:
+        sl.configure(precision=precision)
+        amp, a, g, snr = sl.match_template(sl.DEMGrid(z, 1.0), getattr(WT, cls), scale, age, angle)
+    finally:
+        sl.configure(precision=32)
+    ramp, _, _, rsnr = O.match_template(z, 1.0, 1.0, kind, scale, age, angle)
+    assert a == age and g == angle
+    assert np.array_equal(snr > 0, rsnr > 0) and np.array_equal(amp != 0, ramp != 0)
+    v = rsnr > 0
+    tol = 2e-5 if precision == 32 else 1e-9
+    assert np.abs(amp - ramp)[v].max() <= tol * np.abs(ramp[v]).max()
+    strong = v & (rsnr >= np.median(rsnr[v]))
+    assert (np.abs(snr - rsnr)[strong] / rsnr[strong]).max() < (1e-4 if precision == 32 else 1e-8)
+
+
+def test_search_golden_single_age(emu_lib, golden):
+    """The reference's own golden (scarplet/tests/test_core.py:44-61) through the emulated
+    kernels, at the reference's np.allclose tolerance."""
+    import scarplet_b200 as sl
+    from scarplet_b200.WindowedTemplate import Scarp
+    res = sl.match(sl.DEMGrid(golden.synthetic_dem, 1.0), Scarp, scale=100, age=10,
+                   ang_max=np.pi / 2, ang_min=-np.pi / 2)
+    gold = golden.npz("reference_goldens.npz")["synthetic_match2"]
+    for i in range(4):
+        assert np.allclose(res[i], gold[i])
+
+
+def test_tiles_equal_single_domain(emu_lib):
+    from scarplet_b200 import params as P
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.synth import synthetic_dem
+    from scarplet_b200.templates import Scarp
+    z = synthetic_dem(150, seed=4, nx=170, relief=3.0)
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)[1::30]
+    outs = []
+    for max_fft in (512, 128):
+        with Plan(150, 170, 1.0, 1.0, max_fft=max_fft) as plan:
+            plan.set_dem(z)
+            a, t, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, 10, [2.0, 20.0], angles)
+            plan.reset()
+            plan.sweep(a, t)
+            outs.append(plan.finalize(age_of, angle_of))
+            geo = plan.last_geometry()
+    assert geo["tiles_y"] > 1 and geo["tiles_x"] > 1
+    ref = O.compare((O.match_template(z, 1.0, 1.0, O.SCARP, 10, age, ang)
+                     for age in (2.0, 20.0) for ang in angles), 150, 170)
+    for out in outs:
+        rep = stack_report(out, np.stack(ref))
+        assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.999, rep
+        assert rep["frac_snr_over_tol"] <= 2e-3, rep
+
+
+def test_compare_exact_semantics(emu_lib, golden):
+    import scarplet_b200 as sl
+    r1 = (np.array([[1., 2.], [3., 4.]]), 10., 0.1, np.array([[1., 5.], [2., 0.]]))
+    r2 = (np.array([[5., 6.], [7., 8.]]), 20., 0.2, np.array([[1., 4.], [3., 0.]]))
+    r3 = (np.array([[9., 9.], [9., 9.]]), 30., 0.3, np.array([[.5, 4.], [3., 1.]]))
+    out = np.stack(sl.compare([r1, r2, r3], 2, 2))
+    assert np.array_equal(out, golden.npz("reference_runs.npz")["compare_out"])
+    # planes instead of scalars for age / angle (the age-sweep path of core.match)
+    st = [np.stack([r[0], np.full((2, 2), r[1]), np.full((2, 2), r[2]), r[3]]) for r in (r1, r2, r3)]
+    out2 = np.stack(sl.compare(st, 2, 2))
+    assert np.array_equal(out2, out)
