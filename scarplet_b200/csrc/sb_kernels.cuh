@@ -18,6 +18,10 @@
 #pragma once
 #include "sb_fft.cuh"
 
+#ifndef SB_CONV_BLOCKS
+#define SB_CONV_BLOCKS 3     // resident CTAs per SM targeted by k_conv_cols (complex64)
+#endif
+
 namespace sb {
 
 using sbfft::E;
@@ -127,9 +131,19 @@ SB_DEVICE double template_at(const Tmpl& p, double x, double y) {
         w = sb_mul(sb_div(-xr, p.k0), exp(sb_div(-sb_mul(xr, xr), p.k1)));
     } else {
         // (1 - 2 u^2) * exp(-u^2), u = pi f xr                            :514-515
+        // The Ricker window is as wide as the raster, so the support M = (W != 0) ends
+        // where exp(-u^2) underflows to 0.0 in float64: u^2 >= 1075 ln 2 under IEEE
+        // round-to-nearest (what glibc / NumPy deliver).  A device exp() may round the
+        // last subnormal differently, and one pixel in n is already a 5e-4 SNR error, so
+        // the boundary is decided on u^2 itself.
         const double u = sb_mul(p.k0, xr);
         const double u2 = sb_mul(u, u);
-        w = sb_mul(sb_sub(1.0, sb_mul(2.0, u2)), exp(-u2));
+        double e = 0.0;
+        if (u2 < 745.13321910194122) {
+            e = exp(-u2);
+            if (e == 0.0) e = 4.9406564584124654e-324;
+        }
+        w = sb_mul(sb_sub(1.0, sb_mul(2.0, u2)), e);
     }
     return p.sign < 0 ? -w : w;
 }
@@ -329,19 +343,25 @@ SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int 
 
 // ---------------------------------------------------------------------------
 // k_conv_cols<Py>: grid (ceil(KX / GP), n_templates)
-// gbuf layout: [template][field][out_ny][kpitch] C2
+// gbuf layout: [template][out_ny][kpitch] C4 = (inverse-column plane of t*curv,
+//                                               inverse-column plane of M*curv^2)
+// shared memory per group: exchange buffer (padded_len(N)) + park buffer (N): the first
+// field's result waits in the park buffer (each thread re-reads only what it wrote, so no
+// barrier) until the second is done, and both leave in one 16-byte store.
 // ---------------------------------------------------------------------------
 template <int N, typename R>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : SB_CONV_BLOCKS))
 k_conv_cols(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_base,
-            const typename Vec<R>::v4* SB_RESTRICT trt, const typename Vec<R>::v2* SB_RESTRICT fct, typename Vec<R>::v2* SB_RESTRICT gbuf,
-            const typename Vec<R>::v2* SB_RESTRICT tw) {
+            const typename Vec<R>::v4* SB_RESTRICT trt, const typename Vec<R>::v2* SB_RESTRICT fct,
+            typename Vec<R>::v4* SB_RESTRICT gbuf, const typename Vec<R>::v2* SB_RESTRICT tw) {
     typedef typename Vec<R>::v2 C2;
     typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     constexpr int GP = (T > 256 ? T : 256) / T;
-    C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
+    constexpr int GSM = sbfft::padded_len(N) + N;          // elements of shared memory per group
+    C2* sm = (C2*)sb_shared() + grp * GSM;
+    C2* park = sm + sbfft::padded_len(N);
     const int KX = g.Px / 2 + 1;
     const int kx = sb_bx() * GP + grp;
     const bool active = kx < KX;
@@ -369,18 +389,22 @@ k_conv_cols(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_base
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const C2 w = ld2(spec + t + q * T);
-                const C2 pr = sbfft::cmul(v[q], w);           // core.py:359 / :363
-                v[q] = mk2<R>(pr.y, pr.x);                   // swap: inverse via forward
+                const C2 pr = sbfft::cmul(v[q], w);               // core.py:359 / :363
+                v[q] = mk2<R>(pr.y, pr.x);                        // swap: inverse via forward
             }
         }
         sbfft::forward<N, R>(v, t, sm, tw);
-        if (active) {
-            C2* dst = gbuf + ((long)p_loc * 2 + f) * g.out_ny * g.kpitch + kx;
+        if (f == 0) {
+#pragma unroll
+            for (int q = 0; q < E; ++q) park[t + q * T] = v[q];
+        } else if (active) {
+            C4* dst = gbuf + (long)p_loc * g.out_ny * g.kpitch + kx;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int m = t + q * T;
                 const int io = (m + g.dly) & (N - 1);
-                if (io < g.out_ny) dst[(long)io * g.kpitch] = mk2<R>(v[q].y, v[q].x);
+                const C2 a = park[m];
+                if (io < g.out_ny) dst[(long)io * g.kpitch] = mk4<R>(a.y, a.x, v[q].y, v[q].x);
             }
         }
     }
@@ -397,10 +421,35 @@ struct FitOut {
     double* raw_snr;
 };
 
+// error = (1/n) * (T1 - 2*amp*xcorr + T3) + eps with T1 = ts*amp^2, amp = xcorr/ts
+// (core.py:360-366) is algebraically (T3 - xcorr^2/ts)/n + eps: a cancellation.  In the
+// complex64 pipeline it is evaluated with error-free float32 products (two-term split of
+// xcorr^2 and of 1/ts), which keeps it as accurate as a float64 evaluation of the same
+// float32 inputs without touching the FP64 pipe.
+struct FitScalars {
+    float xn, tn;            // exact powers of two: norm / tscale, norm / c2_scale
+    float its_hi, its_lo;    // 1/ts = hi + lo
+    float inv_n;
+};
+
+SB_DEVICE void fit_pixel(float xraw, float traw, const FitScalars& k, float& amp, float& snr) {
+    const float x = xraw * k.xn;                     // xcorr  (exact scaling)
+    const float t3 = traw * k.tn;                    // T3     (exact scaling)
+    amp = x * k.its_hi;                              // core.py:360
+    const float pp = x * x;
+    const float pe = fmaf(x, x, -pp);                // x*x = pp + pe exactly
+    float num = fmaf(-pp, k.its_hi, t3);             // T3 - x^2/ts
+    num = fmaf(-pp, k.its_lo, num);
+    num = fmaf(-pe, k.its_hi, num);
+    const float t1 = x * amp;                        // core.py:362
+    const float err = fmaf(num, k.inv_n, (float)kEps);   // core.py:366
+    snr = fabsf(t1 / err);                           // core.py:367
+}
+
 template <int N, typename R>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
-           const TSum* SB_RESTRICT sums, const typename Vec<R>::v2* SB_RESTRICT gbuf,
+           const TSum* SB_RESTRICT sums, const typename Vec<R>::v4* SB_RESTRICT gbuf,
            const double* SB_RESTRICT xvec, const double* SB_RESTRICT yvec, FitOut out,
            const typename Vec<R>::v2* SB_RESTRICT tw) {
     typedef typename Vec<R>::v2 C2;
@@ -439,51 +488,63 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
         const Tmpl p = tmpls[tmpl_base + pl];
         if (!raw && (cta_hi < p.i_lo || cta_lo > p.i_hi)) continue;   // whole CTA edge-masked
         const TSum s = sums[pl];
-        const double xc_norm = g.norm / p.tscale, t3_norm = g.norm / g.c2_scale;
-        const C2* gt = gbuf + ((long)pl * 2 + 0) * g.out_ny * g.kpitch + (long)(active ? io : 0) * g.kpitch;
-        const C2* gm = gt + (long)g.out_ny * g.kpitch;
+        const C4* grow = gbuf + ((long)pl * g.out_ny + (active ? io : 0)) * g.kpitch;
         C2 v[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int k = t + q * T;
             const bool direct = k <= N / 2;
             const int kk = direct ? k : N - k;
-            C2 a = mk2<R>((R)0, (R)0), b = mk2<R>((R)0, (R)0);
-            if (active) { a = ld2(gt + kk); b = ld2(gm + kk); }
+            C4 w = mk4<R>((R)0, (R)0, (R)0, (R)0);
+            if (active) w = ld4(grow + kk);
             // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
-            const C2 x = direct ? mk2<R>(a.x - b.y, a.y + b.x)
-                                    : mk2<R>(a.x + b.y, b.x - a.y);
+            const C2 x = direct ? mk2<R>(w.x - w.w, w.y + w.z) : mk2<R>(w.x + w.w, w.z - w.y);
             v[q] = mk2<R>(x.y, x.x);
         }
         sbfft::forward<N, R>(v, t, sm, tw);
+        const bool row_ok = gi >= p.i_lo && gi <= p.i_hi;
+        FitScalars fk;
+        fk.xn = (float)(g.norm / p.tscale);
+        fk.tn = (float)(g.norm / g.c2_scale);
+        fk.its_hi = (float)s.inv_ts;
+        fk.its_lo = (float)(s.inv_ts - (double)fk.its_hi);
+        fk.inv_n = (float)s.inv_n;
+        const double xc_norm = g.norm / p.tscale, t3_norm = g.norm / g.c2_scale;
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             if (gj[q] < 0) continue;
-            const double xc = (double)v[q].y * xc_norm;          // Re ifft: xcorr   core.py:359
-            const double t3 = (double)v[q].x * t3_norm;          // Im ifft: T3      core.py:363
-            double amp = xc * s.inv_ts;                          // core.py:360
-            const double t1 = s.ts * amp * amp;                  // core.py:362
-            const double err = s.inv_n * (t1 - 2.0 * amp * xc + t3) + kEps;   // core.py:366
-            double snr = fabs(t1 / err);                         // core.py:367
+            double amp_d = 0.0, snr_d = 0.0;
+            float amp_f = 0.f, snr_f = 0.f;
+            if (sizeof(R) == 4 && !raw) {
+                fit_pixel((float)v[q].y, (float)v[q].x, fk, amp_f, snr_f);
+            } else {
+                const double xc = (double)v[q].y * xc_norm;          // Re ifft: xcorr   core.py:359
+                const double t3 = (double)v[q].x * t3_norm;          // Im ifft: T3      core.py:363
+                amp_d = xc * s.inv_ts;                               // core.py:360
+                const double t1 = s.ts * amp_d * amp_d;              // core.py:362
+                const double err = s.inv_n * (t1 - 2.0 * amp_d * xc + t3) + kEps;   // core.py:366
+                snr_d = fabs(t1 / err);                              // core.py:367
+                amp_f = (float)amp_d;
+                snr_f = (float)snr_d;
+            }
+            bool kill_snr = false;
             if (p.errmode != 0) {                                // core.py:369-371
                 const double xr = sb_add(sb_mul(sb_ldg(xvec + gj[q]), p.ca), sb_mul(yv, p.sa));
-                if ((p.errmode == 1 && xr <= 0.0) || (p.errmode == 2 && xr >= 0.0)) snr = 0.0;
+                kill_snr = (p.errmode == 1 && xr <= 0.0) || (p.errmode == 2 && xr >= 0.0);
             }
-            if (gi < p.i_lo || gi > p.i_hi || gj[q] < p.j_lo || gj[q] > p.j_hi) {   // core.py:373-375
-                amp = 0.0;
-                snr = 0.0;
-            }
+            const bool masked = !row_ok || gj[q] < p.j_lo || gj[q] > p.j_hi;   // core.py:373-375
+            if (kill_snr || masked) { snr_f = 0.f; snr_d = 0.0; }
+            if (masked) { amp_f = 0.f; amp_d = 0.0; }
             if (raw) {
                 const long o = (long)gi * g.nx + gj[q];
-                out.raw_amp[o] = amp;
-                out.raw_snr[o] = snr;
+                out.raw_amp[o] = amp_d;
+                out.raw_snr[o] = snr_d;
             } else {
-                const float sf = (float)snr;
                 // first maximum wins (core.py:230-240); equal positive SNRs resolve to the
                 // lower flat index so the result does not depend on batch order
-                if (sf > bs[q] || (sf == bs[q] && sf > 0.f && p.idx < bi[q])) {
-                    bs[q] = sf;
-                    ba[q] = (float)amp;
+                if (snr_f > bs[q] || (snr_f == bs[q] && snr_f > 0.f && p.idx < bi[q])) {
+                    bs[q] = snr_f;
+                    ba[q] = amp_f;
                     bi[q] = p.idx;
                 }
             }

@@ -162,6 +162,8 @@ struct Shape {
     static constexpr int threads = T > 256 ? T : 256;
     static constexpr int GP = threads / T;
     static constexpr size_t smem = (size_t)GP * sbfft::padded_len(N) * sizeof(typename Vec<R>::v2);
+    // k_conv_cols adds a park buffer of N elements per group
+    static constexpr size_t smem_conv = (size_t)GP * (sbfft::padded_len(N) + N) * sizeof(typename Vec<R>::v2);
 };
 
 #ifndef SB_EMU
@@ -249,7 +251,8 @@ int plan_axis(const sb_plan* pl, int n, int lo, int hi, AxisPlan* ax) {
     ax->lo = lo;
     ax->hi = hi;
     const int ext = hi - lo + 1;
-    const int max_fft = std::min(pl->max_fft, kMaxFftSupported);
+    // complex128 at 8192 would need 270 KB of shared memory per column in k_conv_cols
+    const int max_fft = std::min(pl->max_fft, pl->precision == 64 ? 4096 : kMaxFftSupported);
     if (is_pow2(n) && n >= kMinFft && n <= max_fft && !pl->force_pad) {
         ax->P = n;
         ax->tiles = 1;
@@ -340,7 +343,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     // batch sizes from the workspace budget
     const int need_rows_max = ay.periodic ? Py : std::min(Py, ay.tile_out + (hi_y - lo_y) + 2);
     const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
-    const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)2 * ay.tile_out * kpitch * sizeof(C2) +
+    const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)ay.tile_out * kpitch * sizeof(C4) +
                             (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
     const size_t budget = (size_t)pl->workspace_mb << 20;
     // templates per angle (max) decides the split of the budget
@@ -361,7 +364,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(C2)));
     SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(C4)));
     SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
-    SB_OK(ensure(pl->gbuf, (size_t)Bt * 2 * ay.tile_out * kpitch * sizeof(C2)));
+    SB_OK(ensure(pl->gbuf, (size_t)Bt * ay.tile_out * kpitch * sizeof(C4)));
     SB_OK(ensure(pl->sums, (size_t)Bt * sizeof(sb::TSum)));
     SB_OK(ensure(pl->tmpls, (size_t)n_tmpls * sizeof(sb::Tmpl)));
     SB_OK(ensure(pl->angles, (size_t)n_angles * sizeof(sb::Angle)));
@@ -438,11 +441,11 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, R>;
                         auto kern = sb::k_conv_cols<N, R>;
-                        SB_ALLOW_SMEM(kern, S::smem);
+                        SB_ALLOW_SMEM(kern, S::smem_conv);
                         ProfScope prof(pl, K_CONV_COLS);
-                        SB_LAUNCH(kern, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem,
+                        SB_LAUNCH(kern, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem_conv,
                                   pl->stream, g, d_tm, pb, a0, (const C4*)pl->trt.p, (const C2*)pl->fct.p,
-                                  (C2*)pl->gbuf.p, twy);
+                                  (C4*)pl->gbuf.p, twy);
                         return check_launch(pl, "k_conv_cols");
                     }));
                     SB_OK(dispatch_n(Px, [&](auto nn) {
@@ -453,7 +456,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                         ProfScope prof(pl, K_FIT_ROWS);
                         SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, cnt, (const sb::TSum*)pl->sums.p,
-                                  (const C2*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
+                                  (const C4*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
                         return check_launch(pl, "k_fit_rows");
                     }));
                 }

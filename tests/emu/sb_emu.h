@@ -166,7 +166,11 @@ typedef void* sb_stream_t;
 #define SB_LAUNCH(kern, grid, block, smem, stream, ...) \
     sbemu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
 
-inline int sb_rt_malloc(void** p, size_t n) { return posix_memalign(p, 256, n ? n : 256) == 0 ? 0 : 2; }
+inline int sb_rt_malloc(void** p, size_t n) {
+    if (posix_memalign(p, 256, n ? n : 256) != 0) return 2;
+    std::memset(*p, 0xFF, n);   // poison (NaN): device memory is uninitialised
+    return 0;
+}
 inline int sb_rt_free(void* p) { std::free(p); return 0; }
 inline int sb_rt_h2d(void* d, const void* h, size_t n, sb_stream_t) { std::memcpy(d, h, n); return 0; }
 inline int sb_rt_d2h(void* h, const void* d, size_t n, sb_stream_t) { std::memcpy(h, d, n); return 0; }

@@ -101,6 +101,20 @@ def test_template_support_matches_oracle(cuda_lib):
             assert np.allclose(t, ref, rtol=1e-12, atol=1e-300)
 
 
+def test_ricker_support_at_exp_underflow(cuda_lib):
+    """The Ricker support ends where float64 exp(-u^2) underflows (u^2 ~ 745.13); n counts
+    those pixels, so the device must draw the line exactly where NumPy does: every
+    orientation of the 1-degree grid, support equal pixel for pixel."""
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.templates import Channel
+    from oracle import scarplet_oracle as O
+    with Plan(257, 255, 1.0, 1.0) as plan:
+        for angle in O.search_angles():
+            t = plan.render_template(Channel._sb_spec, 8, 0.15, angle)
+            ref = O.template_array(O.RICKER, 8, 0.15, angle, 255, 257, 1.0)
+            assert np.array_equal(t != 0, ref != 0), angle
+
+
 def test_match_template_golden_all_masked(cuda_lib, golden):
     """synthetic_match3.npy: scale 100 at angle 0 on 200x200 masks everything."""
     import scarplet_b200 as sl
