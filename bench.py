@@ -223,6 +223,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     with torch.cuda.stream(stream):
         plan = Plan(n, n, 1.0, 1.0, device=local, stream=stream.cuda_stream)
+        if args.fast is not None:
+            plan.set_option("fast", args.fast)
         plan.set_dem(z_pinned.numpy())                       # inputs resident in HBM
         lo, hi = D.shard_bounds(len(angles), world, rank)
         a_rec, t_rec, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, wl["scale"], ages, angles,
@@ -373,6 +375,7 @@ def main():
     ap.add_argument("--ages", type=int, default=30)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast", type=int, default=None, help="developer switch: 0 = simple kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

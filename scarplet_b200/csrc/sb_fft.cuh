@@ -144,44 +144,111 @@ template <typename R> struct Dft<R, 16> {
     }
 };
 
-// ---- one Stockham stage ----------------------------------------------------
-// v[q] = x[t + q*T] on entry.  On exit the same layout holds the stage output
-// (after the exchange for all but the last stage).
+// ---- one Stockham stage, split into its four parts ----------------------------
+// v[q] = x[t + q*T].  A stage is: fetch the thread's twiddles (global, L1-resident),
+// multiply + radix butterflies in registers, scatter to the exchange buffer in the
+// order the next stage reads, gather v[q] = sm[t + q*T].  Kernels that pipeline two
+// transforms (sb_kernels.cuh, "leapfrog") call the parts; `stage` strings them
+// together for the simple one-transform-at-a-time kernels.
+constexpr int TW = E - 1;    // twiddle registers a thread needs for one stage (at most)
+
+template <int N, int S, typename R>
+SB_DEVICE void load_tw(typename Vec<R>::v2 (&w)[TW], int t, const typename Vec<R>::v2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    constexpr int RADIX = stage_radix(N, S);
+    constexpr int NS = stage_ns(N, S);
+    constexpr int B = E / RADIX;
+    constexpr int TWO = twiddle_offset(N, S);
+    if (S == 0) return;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int k = (t + m * T) & (NS - 1);
+#pragma unroll
+        for (int u = 1; u < RADIX; ++u) w[(u - 1) * B + m] = ld2(tw + TWO + (u - 1) * NS + k);
+    }
+}
+
+template <int N, int S, typename R>
+SB_DEVICE void stage_math(typename Vec<R>::v2 (&v)[E], const typename Vec<R>::v2 (&w)[TW]) {
+    typedef typename Vec<R>::v2 C;
+    constexpr int RADIX = stage_radix(N, S);
+    constexpr int B = E / RADIX;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        C x[RADIX];
+#pragma unroll
+        for (int u = 0; u < RADIX; ++u) x[u] = v[m + u * B];
+        if (S > 0) {
+#pragma unroll
+            for (int u = 1; u < RADIX; ++u) x[u] = cmul(x[u], w[(u - 1) * B + m]);
+        }
+        Dft<R, RADIX>::run(x);
+#pragma unroll
+        for (int u = 0; u < RADIX; ++u) v[m + u * B] = x[u];
+    }
+}
+
+template <int N, int S, typename R>
+SB_DEVICE void stage_store(const typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm) {
+    constexpr int T = N / E;
+    constexpr int RADIX = stage_radix(N, S);
+    constexpr int NS = stage_ns(N, S);
+    constexpr int B = E / RADIX;
+#pragma unroll
+    for (int m = 0; m < B; ++m) {
+        const int j = t + m * T;
+        const int base = (j / NS) * (NS * RADIX) + (j & (NS - 1));
+#pragma unroll
+        for (int u = 0; u < RADIX; ++u) sm[pad_index(base + u * NS)] = v[m + u * B];
+    }
+}
+
+template <int N, typename R>
+SB_DEVICE void stage_load(typename Vec<R>::v2 (&v)[E], int t, const typename Vec<R>::v2* sm) {
+    constexpr int T = N / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) v[q] = sm[pad_index(t + q * T)];
+}
+
+// First stage (radix 16, no twiddles) when only v[0] and v[15] are non-zero: the
+// column transform of a template whose support is shorter than T on either side of
+// the origin.  X[u] = v0 + v15 * W16^(-u): 8 constant products instead of a full DFT16.
+template <typename R>
+SB_DEVICE void stage0_sparse2(typename Vec<R>::v2 (&v)[E]) {
+    typedef typename Vec<R>::v2 C;
+    const R h = (R)0.70710678118654752440;
+    const R c1 = (R)0.92387953251128675613;
+    const R s1 = (R)0.38268343236508977173;
+    const C a = v[0], b = v[E - 1];
+    C p[8];
+    const R cx = c1 * b.x, cy = c1 * b.y, sx = s1 * b.x, sy = s1 * b.y, hx = h * b.x, hy = h * b.y;
+    p[0] = b;
+    p[1] = mk2<R>(cx - sy, cy + sx);
+    p[2] = mk2<R>(hx - hy, hx + hy);
+    p[3] = mk2<R>(sx - cy, sy + cx);
+    p[4] = mk2<R>(-b.y, b.x);
+    p[5] = mk2<R>(-sx - cy, cx - sy);
+    p[6] = mk2<R>(-hx - hy, hx - hy);
+    p[7] = mk2<R>(-cx - sy, sx - cy);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        v[u] = cadd(a, p[u]);
+        v[u + 8] = csub(a, p[u]);
+    }
+}
+
 template <int N, int S, typename R>
 SB_DEVICE void stage(typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm,
                      const typename Vec<R>::v2* SB_RESTRICT tw) {
     typedef typename Vec<R>::v2 C;
-    constexpr int T = N / E;
-    constexpr int RADIX = stage_radix(N, S);
-    constexpr int NS = stage_ns(N, S);
-    constexpr int B = E / RADIX;             // butterflies per thread
-    constexpr bool LAST = (NS * RADIX == N);
-    constexpr int TWO = twiddle_offset(N, S);
-#pragma unroll
-    for (int m = 0; m < B; ++m) {
-        const int j = t + m * T;             // butterfly index in [0, N/RADIX)
-        C x[RADIX];
-#pragma unroll
-        for (int u = 0; u < RADIX; ++u) x[u] = v[m + u * B];
-        if (NS > 1) {
-            const int k = j & (NS - 1);
-#pragma unroll
-            for (int u = 1; u < RADIX; ++u) x[u] = cmul(x[u], ld2(tw + TWO + (u - 1) * NS + k));
-        }
-        Dft<R, RADIX>::run(x);
-        if (LAST) {
-#pragma unroll
-            for (int u = 0; u < RADIX; ++u) v[m + u * B] = x[u];
-        } else {
-            const int base = (j / NS) * (NS * RADIX) + (j & (NS - 1));
-#pragma unroll
-            for (int u = 0; u < RADIX; ++u) sm[pad_index(base + u * NS)] = x[u];
-        }
-    }
+    constexpr bool LAST = (stage_ns(N, S) * stage_radix(N, S) == N);
+    C w[TW];
+    load_tw<N, S, R>(w, t, tw);
+    stage_math<N, S, R>(v, w);
     if (!LAST) {
+        stage_store<N, S, R>(v, t, sm);
         sb_sync();
-#pragma unroll
-        for (int q = 0; q < E; ++q) v[q] = sm[pad_index(t + q * T)];
+        stage_load<N, R>(v, t, sm);
         sb_sync();
     }
 }

@@ -43,6 +43,7 @@ struct Geom {
     double dx, dx2, dy2;     // cell size, dx**2, dy**2 as the host computes them
     double norm;             // 1 / (Px * Py)
     double c2_scale;         // power of two: curv**2 is packed as curv**2 * c2_scale next to curv
+    int dbg;                 // developer ablation switches (SB_DBG), 0 in production
 };
 
 struct Angle {               // one search orientation (curvature direction)
@@ -71,6 +72,23 @@ struct TSum {                // per-template scalars produced by k_tmpl_sums
 };
 
 constexpr double kEps = 2.220446049250313e-16;   // np.spacing(1), core.py:339
+
+// per-template scalars of the float32 epilogue of k_fit_rows_f (written by k_tmpl_sums)
+struct FitT {
+    float xn, tn;            // exact powers of two: norm / tscale, norm / c2_scale
+    float its_hi, its_lo;    // 1/ts = hi + lo
+    float inv_n;
+    int i_lo, i_hi, j_lo, j_hi;   // un-masked output window (core.py:373-375)
+    int idx;                 // flat result index
+};
+
+// gbuf (the inverse-column planes handed from the column kernel to the row kernel) holds,
+// per template, Py domain rows m of kpitch C4 elements, two rows interleaved:
+// [m / 2][kx][m & 1].  The column kernel has rows m, m + 1 in adjacent lanes, so a warp
+// store fills whole 32-byte sectors (a 16-byte half-sector store runs at 0.9 TB/s on
+// B200, a full-sector one at 4.7 TB/s: scratch/ubench_scatter.cu); the row kernel reads
+// its row at a 32-byte stride.
+SB_DEVICE long gbuf_index(int m, int kx, int kpitch) { return ((long)(m >> 1) * kpitch + kx) * 2 + (m & 1); }
 
 SB_DEVICE int wrap(int v, int n) {
     int r = v % n;
@@ -322,7 +340,7 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
 
 // one thread per template: fixed-order sum of the per-row partials
 SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
-                      const double2* SB_RESTRICT part, TSum* SB_RESTRICT sums) {
+                      const double2* SB_RESTRICT part, TSum* SB_RESTRICT sums, FitT* SB_RESTRICT fit) {
     const int p_loc = sb_bx() * 32 + sb_tid();
     if (p_loc >= count) return;
     const Tmpl p = tmpls[tmpl_base + p_loc];
@@ -339,6 +357,17 @@ SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int 
     s.inv_n = 1.0 / s.n_eps;
     s.inv_ts = 1.0 / ts;
     sums[p_loc] = s;
+    if (fit) {
+        FitT k;
+        k.xn = (float)(g.norm / p.tscale);
+        k.tn = (float)(g.norm / g.c2_scale);
+        k.its_hi = (float)s.inv_ts;
+        k.its_lo = (float)(s.inv_ts - (double)k.its_hi);
+        k.inv_n = (float)s.inv_n;
+        k.i_lo = p.i_lo; k.i_hi = p.i_hi; k.j_lo = p.j_lo; k.j_hi = p.j_hi;
+        k.idx = p.idx;
+        fit[p_loc] = k;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -398,13 +427,13 @@ k_conv_cols(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_base
 #pragma unroll
             for (int q = 0; q < E; ++q) park[t + q * T] = v[q];
         } else if (active) {
-            C4* dst = gbuf + (long)p_loc * g.out_ny * g.kpitch + kx;
+            C4* dst = gbuf + (long)p_loc * N * g.kpitch;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 const int m = t + q * T;
                 const int io = (m + g.dly) & (N - 1);
                 const C2 a = park[m];
-                if (io < g.out_ny) dst[(long)io * g.kpitch] = mk4<R>(a.y, a.x, v[q].y, v[q].x);
+                if (io < g.out_ny) dst[gbuf_index(m, kx, g.kpitch)] = mk4<R>(a.y, a.x, v[q].y, v[q].x);
             }
         }
     }
@@ -488,7 +517,7 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
         const Tmpl p = tmpls[tmpl_base + pl];
         if (!raw && (cta_hi < p.i_lo || cta_lo > p.i_hi)) continue;   // whole CTA edge-masked
         const TSum s = sums[pl];
-        const C4* grow = gbuf + ((long)pl * g.out_ny + (active ? io : 0)) * g.kpitch;
+        const C4* grow = gbuf + (long)pl * g.Py * g.kpitch + gbuf_index(((active ? io : 0) - g.dly) & (g.Py - 1), 0, g.kpitch);
         C2 v[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
@@ -496,7 +525,7 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
             const bool direct = k <= N / 2;
             const int kk = direct ? k : N - k;
             C4 w = mk4<R>((R)0, (R)0, (R)0, (R)0);
-            if (active) w = ld4(grow + kk);
+            if (active) w = ld4(grow + 2 * kk);
             // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
             const C2 x = direct ? mk2<R>(w.x - w.w, w.y + w.z) : mk2<R>(w.x + w.w, w.z - w.y);
             v[q] = mk2<R>(x.y, x.x);

@@ -3,12 +3,14 @@
 #include "../../include/scarplet_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <type_traits>
 #include <vector>
 
 #include "sb_kernels.cuh"
+#include "sb_fast.cuh"
 
 static_assert(sizeof(sb_template) == sizeof(sb::Tmpl), "sb_template / sb::Tmpl layout");
 static_assert(sizeof(sb_angle) == sizeof(sb::Angle), "sb_angle / sb::Angle layout");
@@ -79,7 +81,8 @@ struct sb_plan {
     int* d_bidx = nullptr;
     std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
-    Buf cr, fct, trt, part, gbuf, sums, tmpls, angles, tables, raw;
+    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw;
+    int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     long launches = 0;
     double c2_scale = 1.0;
     int profile = 0;
@@ -164,6 +167,11 @@ struct Shape {
     static constexpr size_t smem = (size_t)GP * sbfft::padded_len(N) * sizeof(typename Vec<R>::v2);
     // k_conv_cols adds a park buffer of N elements per group
     static constexpr size_t smem_conv = (size_t)GP * (sbfft::padded_len(N) + N) * sizeof(typename Vec<R>::v2);
+    // pipelined kernels (sb_fast.cuh): two exchange buffers per group; k_fit_rows_f adds the
+    // batch's scalars, the active-template list (+ its length) and the flags
+    static constexpr size_t smem_conv_f = (size_t)GP * 2 * sbfft::padded_len(N) * sizeof(float2);
+    static constexpr size_t smem_fit_f = smem_conv_f + sb::kFitMaxBatch * sizeof(sb::FitT) +
+                                         (2 * sb::kFitMaxBatch + 1) * sizeof(int);
 };
 
 #ifndef SB_EMU
@@ -343,7 +351,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     // batch sizes from the workspace budget
     const int need_rows_max = ay.periodic ? Py : std::min(Py, ay.tile_out + (hi_y - lo_y) + 2);
     const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
-    const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)ay.tile_out * kpitch * sizeof(C4) +
+    const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)Py * kpitch * sizeof(C4) +
                             (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
     const size_t budget = (size_t)pl->workspace_mb << 20;
     // templates per angle (max) decides the split of the budget
@@ -359,13 +367,15 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     Ba = std::min(Ba, 64);
     if (max_per_angle == 1) Bt = std::min(Bt, Ba), Ba = std::min(Ba, Bt);
     Bt = std::min(Bt, n_tmpls);
+    if (Bt > 1) Bt &= ~1;            // k_fit_rows_f walks the batch two templates at a time
 
     SB_OK(ensure(pl->cr, (size_t)Ba * need_rows_max * kpitch * sizeof(C4)));
     SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(C2)));
     SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(C4)));
     SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
-    SB_OK(ensure(pl->gbuf, (size_t)Bt * ay.tile_out * kpitch * sizeof(C4)));
+    SB_OK(ensure(pl->gbuf, (size_t)Bt * Py * kpitch * sizeof(C4)));
     SB_OK(ensure(pl->sums, (size_t)Bt * sizeof(sb::TSum)));
+    SB_OK(ensure(pl->fit, (size_t)Bt * sizeof(sb::FitT)));
     SB_OK(ensure(pl->tmpls, (size_t)n_tmpls * sizeof(sb::Tmpl)));
     SB_OK(ensure(pl->angles, (size_t)n_angles * sizeof(sb::Angle)));
     SB_TRY(sb_rt_h2d(pl->tmpls.p, tm.data(), (size_t)n_tmpls * sizeof(sb::Tmpl), pl->stream));
@@ -392,6 +402,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
             g.dx = pl->dx; g.dx2 = pl->dx2; g.dy2 = pl->dy2;
             g.norm = 1.0 / ((double)Px * (double)Py);
             g.c2_scale = pl->c2_scale;
+            g.dbg = std::getenv("SB_DBG") ? std::atoi(std::getenv("SB_DBG")) : 0;
             const int need_rows = g.need_y_hi - g.need_y_lo + 1;
 
             for (int a0 = 0; a0 < n_angles; a0 += Ba) {
@@ -434,9 +445,53 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                     {
                         ProfScope prof(pl, K_TMPL_SUMS);
                         SB_LAUNCH(sb::k_tmpl_sums, dim3(div_up(cnt, 32)), dim3(32), 0, pl->stream, g, d_tm, pb, cnt,
-                                  (const double2*)pl->part.p, (sb::TSum*)pl->sums.p);
+                                  (const double2*)pl->part.p, (sb::TSum*)pl->sums.p, (sb::FitT*)pl->fit.p);
                         SB_OK(check_launch(pl, "k_tmpl_sums"));
                     }
+                    bool err_masks = false;
+                    for (int i = pb; i < pb + cnt; ++i) err_masks |= tm[i].errmode != 0;
+                    const bool fast = std::is_same<R, float>::value && pl->fast;
+                    const bool fast_fit = fast && !so.raw_amp && !err_masks && cnt <= sb::kFitMaxBatch;
+                    if constexpr (std::is_same<R, float>::value) {
+                        if (fast) {
+                            SB_OK(dispatch_n(Py, [&](auto nn) {
+                                constexpr int N = decltype(nn)::value;
+                                using S = Shape<N, float>;
+                                // every template column has at most two non-zero inputs per thread
+                                const bool sparse = hi_y <= S::T - 1 && lo_y >= -S::T;
+                                ProfScope prof(pl, K_CONV_COLS);
+                                const dim3 grid(cnt, div_up(KX, S::GP));
+                                if (sparse) {
+                                    auto kern = sb::k_conv_cols_f<N, true>;
+                                    SB_ALLOW_SMEM(kern, S::smem_conv_f);
+                                    SB_LAUNCH(kern, grid, dim3(S::threads), S::smem_conv_f, pl->stream, g, d_tm, pb, a0,
+                                              (const float4*)pl->trt.p, (const float2*)pl->fct.p, (float4*)pl->gbuf.p,
+                                              (const float2*)twy);
+                                } else {
+                                    auto kern = sb::k_conv_cols_f<N, false>;
+                                    SB_ALLOW_SMEM(kern, S::smem_conv_f);
+                                    SB_LAUNCH(kern, grid, dim3(S::threads), S::smem_conv_f, pl->stream, g, d_tm, pb, a0,
+                                              (const float4*)pl->trt.p, (const float2*)pl->fct.p, (float4*)pl->gbuf.p,
+                                              (const float2*)twy);
+                                }
+                                return check_launch(pl, "k_conv_cols_f");
+                            }));
+                        }
+                        if (fast_fit) {
+                            SB_OK(dispatch_n(Px, [&](auto nn) {
+                                constexpr int N = decltype(nn)::value;
+                                using S = Shape<N, float>;
+                                auto kern = sb::k_fit_rows_f<N>;
+                                SB_ALLOW_SMEM(kern, S::smem_fit_f);
+                                ProfScope prof(pl, K_FIT_ROWS);
+                                SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem_fit_f,
+                                          pl->stream, g, cnt, (const sb::FitT*)pl->fit.p, (const float4*)pl->gbuf.p,
+                                          pl->d_bsnr, pl->d_bamp, pl->d_bidx, (const float2*)twx);
+                                return check_launch(pl, "k_fit_rows_f");
+                            }));
+                        }
+                    }
+                    if (!fast) {
                     SB_OK(dispatch_n(Py, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, R>;
@@ -448,6 +503,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                   (C4*)pl->gbuf.p, twy);
                         return check_launch(pl, "k_conv_cols");
                     }));
+                    }
+                    if (!fast_fit) {
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, R>;
@@ -459,6 +516,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                   (const C4*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
                         return check_launch(pl, "k_fit_rows");
                     }));
+                    }
                 }
             }
         }
@@ -547,7 +605,7 @@ int sb_plan_destroy(sb_plan* pl) {
     if (pl->d_bidx) sb_rt_free(pl->d_bidx);
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
     for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
-    for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->tmpls, &pl->angles,
+    for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
                    &pl->tables, &pl->raw})
         release(*b);
 #ifndef SB_EMU
@@ -569,6 +627,7 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
     }
     if (k == "force_pad") { pl->force_pad = value != 0; return 0; }
     if (k == "profile") { pl->profile = value != 0; return 0; }
+    if (k == "fast") { pl->fast = value != 0; return 0; }
     if (k == "precision") {
         if (value != 32 && value != 64) return fail("precision must be 32 or 64");
         pl->precision = (int)value;

@@ -36,6 +36,22 @@ SB_DEVICE void* sb_shared() {
     return sb_smem_raw;
 }
 template <typename T> SB_DEVICE T sb_ldg(const T* p) { return __ldg(p); }
+// read-once data (spectra, intermediate planes): do not let it evict the twiddle tables from L1
+SB_DEVICE float2 sb_ld_stream(const float2* p) {
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+SB_DEVICE float4 sb_ld_stream(const float4* p) {
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+// hint: pull one 128-byte line towards L2 ahead of the loads that will need it
+SB_DEVICE void sb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// a / b to ~2 ulp (MUFU.RCP + multiply); used where the tolerance is 1e-4
+SB_DEVICE float sb_fdiv_fast(float a, float b) { return __fdividef(a, b); }
 
 // IEEE operations that must not be contracted into FMAs (bit-exact float64
 // parity with NumPy for the curvature stencil and the template window).

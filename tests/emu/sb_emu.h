@@ -154,6 +154,10 @@ SB_DEVICE void sb_sync() {
 }
 SB_DEVICE void* sb_shared() { return sbemu::current()->smem; }
 template <typename T> SB_DEVICE T sb_ldg(const T* p) { return *p; }
+SB_DEVICE void sb_prefetch_l2(const void*) {}
+SB_DEVICE float2 sb_ld_stream(const float2* p) { return *p; }
+SB_DEVICE float4 sb_ld_stream(const float4* p) { return *p; }
+SB_DEVICE float sb_fdiv_fast(float a, float b) { return a / b; }
 
 // built with -ffp-contract=off, so these stay separate IEEE operations
 SB_DEVICE double sb_mul(double a, double b) { return a * b; }
