@@ -217,7 +217,7 @@ SB_DEVICE void fit_pixel_fast(float xraw, float traw, const FitT& k, float& amp,
     snr = fabsf(sb_fdiv_fast(t1, err));              // core.py:367
 }
 
-template <int N>
+template <int N, bool PAIRED>
 struct FitCtx {
     static constexpr int K = sbfft::num_stages(N);
     static constexpr int T = N / E;
@@ -282,7 +282,9 @@ struct FitCtx {
                 bool direct = q < E / 2;
                 int kk = q < E / 2 ? t + q * T : N - (t + q * T);
                 if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
-                if (row) g4 = (dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)q) : sb_ld_stream(row + 2 * kk);
+                // PAIRED: the CTA's other row group reads the other half of each sector
+                if (row) g4 = (dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)q)
+                              : PAIRED ? sb_ld_shared_soon(row + 2 * kk) : sb_ld_stream(row + 2 * kk);
                 v[q] = direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
             }
         }
@@ -317,15 +319,18 @@ struct FitCtx {
     template <int F> SB_DEVICE void load(float2 (&v)[E]) { sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB); }
 };
 
-template <int N>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+// MINT: threads per CTA when one row needs fewer.  512 puts the two rows that share every
+// 32-byte sector of the interleaved planes into the same CTA.
+template <int N, int MINT>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > MINT ? N / E : MINT), ((N / E > MINT ? N / E : MINT) > 256 ? 1 : 2))
 k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RESTRICT gbuf,
              float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
              const float2* SB_RESTRICT tw) {
     constexpr int T = N / E;
-    constexpr int THREADS = T > 256 ? T : 256;
+    constexpr int THREADS = T > MINT ? T : MINT;
     constexpr int GP = THREADS / T;
     constexpr int PL = sbfft::padded_len(N);
+    typedef FitCtx<N, (GP > 1)> Ctx;
     const int grp = sb_tid() / T, t = sb_tid() % T;
     float2* sm = (float2*)sb_shared();
     FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
@@ -355,7 +360,7 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
 
     float bs[E], ba[E];
     unsigned bw[E / 4];
-    FitCtx<N> c(bs, ba, bw);
+    Ctx c(bs, ba, bw);
     c.t = t;
     c.smA = sm + (long)grp * 2 * PL;
     c.smB = c.smA + PL;
@@ -405,13 +410,13 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
         float2 va[E], vb[E];
         // no barrier between pairs: buffer A was last read before the pair's final barrier,
         // buffer B is next written after the coming pair's first barrier
-        leapfrog<FitCtx<N>::K>(c, va, vb);
+        leapfrog<Ctx::K>(c, va, vb);
     }
 #pragma unroll
     for (int q = 0; q < E; ++q) {
         const int jo = (t + q * T + g.dlx) & (N - 1);
         const unsigned slot = c.slot_of(q);
-        if (active && jo < g.out_nx && slot != FitCtx<N>::kNoSlot) {
+        if (active && jo < g.out_nx && slot != Ctx::kNoSlot) {
             const long o = (long)gi * g.nx + g.ox + jo;
             best_snr[o] = bs[q];
             best_amp[o] = ba[q];

@@ -103,36 +103,62 @@ SB_DEVICE double zfill(const double* SB_RESTRICT z, long i) {
     return v != v ? 0.0 : v;            // dem.py:85-86
 }
 
-SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int i, int j,
-                              double dx, double dx2, double dy2, const Angle& a) {
+// the three angle-independent second differences (dem.py:88-99); NaN centre -> NaN dxx
+struct Diff3 { double dxx, dxy, dyy; };
+
+SB_DEVICE Diff3 second_differences_at(const double* SB_RESTRICT z, int ny, int nx, int i, int j,
+                                      double dx, double dx2, double dy2) {
     const long o = (long)i * nx + j;
-    const double zc_raw = sb_ldg(z + o);
-    if (zc_raw != zc_raw) return zc_raw;            // dem.py:105
-    const double zc = zc_raw;
-    double dxx = 0.0, dyy = 0.0, dxy = 0.0;
+    const double zc = sb_ldg(z + o);
+    Diff3 r;
+    r.dxx = 0.0; r.dyy = 0.0; r.dxy = 0.0;
+    if (zc != zc) { r.dxx = zc; return r; }         // dem.py:105
     const bool jm = j >= 1, jp = j <= nx - 2, im = i >= 1, ip = i <= ny - 2;
     double zl = 0.0, zu = 0.0;
     if (jm) zl = zfill(z, o - 1);
     if (im) zu = zfill(z, o - nx);
     if (jm && jp) {
         const double zr = zfill(z, o + 1);
-        dxx = sb_div(sb_sub(sb_sub(zr, zc), sb_sub(zc, zl)), dx2);       // dem.py:95
+        r.dxx = sb_div(sb_sub(sb_sub(zr, zc), sb_sub(zc, zl)), dx2);       // dem.py:95
     }
     if (im && ip) {
         const double zd = zfill(z, o + nx);
-        dyy = sb_div(sb_sub(sb_sub(zd, zc), sb_sub(zc, zu)), dy2);       // dem.py:99
+        r.dyy = sb_div(sb_sub(sb_sub(zd, zc), sb_sub(zc, zu)), dy2);       // dem.py:99
     }
     if (im && jm) {
         const double zul = zfill(z, o - nx - 1);
         const double g1 = sb_div(sb_sub(zc, zl), dx);                    // dem.py:88
         const double g0 = sb_div(sb_sub(zu, zul), dx);
-        dxy = sb_div(sb_sub(g1, g0), dx);                                // dem.py:89
+        r.dxy = sb_div(sb_sub(g1, g0), dx);                              // dem.py:89
     }
-    // dem.py:103-104, left to right
+    return r;
+}
+
+// dem.py:103-104, left to right; a NaN dxx (NaN DEM cell) propagates
+SB_DEVICE double combine_curvature(double dxx, double dxy, double dyy, const Angle& a) {
     const double t0 = sb_mul(dxx, a.ca2);
     const double t1 = sb_mul(sb_mul(sb_mul(2.0, dxy), a.sa), a.ca);
     const double t2 = sb_mul(dyy, a.sa2);
     return sb_add(sb_sub(t0, t1), t2);
+}
+
+SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int i, int j,
+                              double dx, double dx2, double dy2, const Angle& a) {
+    const Diff3 d = second_differences_at(z, ny, nx, i, j, dx, dx2, dy2);
+    if (d.dxx != d.dxx) return d.dxx;
+    return combine_curvature(d.dxx, d.dxy, d.dyy, a);
+}
+
+// the DEM's second differences, computed once per DEM: planes [dxx][dxy][dyy] of ny*nx
+SB_GLOBAL k_second_differences(int ny, int nx, const double* SB_RESTRICT dem, double dx, double dx2,
+                               double dy2, double* SB_RESTRICT out) {
+    const long n = (long)ny * nx;
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    const Diff3 d = second_differences_at(dem, ny, nx, (int)(i / nx), (int)(i % nx), dx, dx2, dy2);
+    out[i] = d.dxx;
+    out[n + i] = d.dxy;
+    out[2 * n + i] = d.dyy;
 }
 
 // ---------------------------------------------------------------------------
@@ -200,7 +226,7 @@ SB_DEVICE void hermitian_split(const typename Vec<R>::v2 (&v)[E], int t, typenam
 // ---------------------------------------------------------------------------
 template <int N, typename R>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
-k_curv_rows(Geom g, const double* SB_RESTRICT dem, const Angle* SB_RESTRICT angles, int angle_base,
+k_curv_rows(Geom g, const double* SB_RESTRICT diffs, const Angle* SB_RESTRICT angles, int angle_base,
             typename Vec<R>::v4* SB_RESTRICT cr, const typename Vec<R>::v2* SB_RESTRICT tw) {
     typedef typename Vec<R>::v2 C2;
     typedef typename Vec<R>::v4 C4;
@@ -222,7 +248,8 @@ k_curv_rows(Geom g, const double* SB_RESTRICT dem, const Angle* SB_RESTRICT angl
         C2 val = mk2<R>((R)0, (R)0);
         if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
             const int gj = wrap(g.ox + sx, g.nx);
-            const double c = curvature_at(dem, g.ny, g.nx, gi, gj, g.dx, g.dx2, g.dy2, ang);
+            const long o = (long)gi * g.nx + gj, n = (long)g.ny * g.nx;
+            const double c = combine_curvature(sb_ldg(diffs + o), sb_ldg(diffs + n + o), sb_ldg(diffs + 2 * n + o), ang);
             val = mk2<R>((R)c, (R)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
         }
         v[q] = val;

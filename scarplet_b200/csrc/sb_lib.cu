@@ -74,6 +74,7 @@ struct sb_plan {
     bool own_stream = false;
     double* d_dem = nullptr;
     bool own_dem = false;
+    double* d_diffs = nullptr;      // dxx, dxy, dyy planes of the current DEM (dem.py:88-99)
     double* d_x = nullptr;
     double* d_y = nullptr;
     float* d_bsnr = nullptr;
@@ -83,6 +84,7 @@ struct sb_plan {
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
     Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
+    int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 256;
     long launches = 0;
     double c2_scale = 1.0;
     int profile = 0;
@@ -235,6 +237,13 @@ void drain_profile(sb_plan* pl) {
 
 // curvature RMS -> power-of-two factor that brings curv**2 to the magnitude of curv
 int update_curv_scale(sb_plan* pl) {
+    {   // the angle-independent second differences, once per DEM
+        const long n = (long)pl->ny * pl->nx;
+        if (!pl->d_diffs) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs, (size_t)n * 3 * sizeof(double)));
+        SB_LAUNCH(sb::k_second_differences, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx,
+                  (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, pl->d_diffs);
+        SB_OK(check_launch(pl, "k_second_differences"));
+    }
     const int blocks = std::max(1, std::min(1024, div_up((long)pl->ny * pl->nx, 256)));
     SB_OK(ensure(pl->raw, (size_t)blocks * sizeof(double)));
     SB_LAUNCH(sb::k_curv_sumsq, dim3(blocks), dim3(256), 256 * sizeof(double), pl->stream, pl->ny, pl->nx,
@@ -416,7 +425,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                     SB_ALLOW_SMEM(kern, S::smem);
                     ProfScope prof(pl, K_CURV_ROWS);
                     SB_LAUNCH(kern, dim3(div_up(need_rows, S::GP), a1 - a0), dim3(S::threads),
-                              S::smem, pl->stream, g, (const double*)pl->d_dem, d_an, a0, (C4*)pl->cr.p, twx);
+                              S::smem, pl->stream, g, (const double*)pl->d_diffs, d_an, a0, (C4*)pl->cr.p, twx);
                     return check_launch(pl, "k_curv_rows");
                 }));
                 SB_OK(dispatch_n(Py, [&](auto nn) {
@@ -481,12 +490,25 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                             SB_OK(dispatch_n(Px, [&](auto nn) {
                                 constexpr int N = decltype(nn)::value;
                                 using S = Shape<N, float>;
-                                auto kern = sb::k_fit_rows_f<N>;
-                                SB_ALLOW_SMEM(kern, S::smem_fit_f);
                                 ProfScope prof(pl, K_FIT_ROWS);
-                                SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem_fit_f,
-                                          pl->stream, g, cnt, (const sb::FitT*)pl->fit.p, (const float4*)pl->gbuf.p,
-                                          pl->d_bsnr, pl->d_bamp, pl->d_bidx, (const float2*)twx);
+                                if (S::T <= 256 && pl->fit_threads == 512) {
+                                    constexpr int threads = S::T > 512 ? S::T : 512;
+                                    constexpr int GP = threads / S::T;
+                                    constexpr size_t smem = S::smem_fit_f - S::smem_conv_f +
+                                                            (size_t)GP * 2 * sbfft::padded_len(N) * sizeof(float2);
+                                    auto kern = sb::k_fit_rows_f<N, 512>;
+                                    SB_ALLOW_SMEM(kern, smem);
+                                    SB_LAUNCH(kern, dim3(div_up(g.out_ny, GP)), dim3(threads), smem, pl->stream, g, cnt,
+                                              (const sb::FitT*)pl->fit.p, (const float4*)pl->gbuf.p, pl->d_bsnr,
+                                              pl->d_bamp, pl->d_bidx, (const float2*)twx);
+                                } else {
+                                    auto kern = sb::k_fit_rows_f<N, 256>;
+                                    SB_ALLOW_SMEM(kern, S::smem_fit_f);
+                                    SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem_fit_f,
+                                              pl->stream, g, cnt, (const sb::FitT*)pl->fit.p,
+                                              (const float4*)pl->gbuf.p, pl->d_bsnr, pl->d_bamp, pl->d_bidx,
+                                              (const float2*)twx);
+                                }
                                 return check_launch(pl, "k_fit_rows_f");
                             }));
                         }
@@ -598,6 +620,7 @@ int sb_plan_destroy(sb_plan* pl) {
 #endif
     sb_rt_sync(pl->stream);
     if (pl->own_dem && pl->d_dem) sb_rt_free(pl->d_dem);
+    if (pl->d_diffs) sb_rt_free(pl->d_diffs);
     if (pl->d_x) sb_rt_free(pl->d_x);
     if (pl->d_y) sb_rt_free(pl->d_y);
     if (pl->d_bsnr) sb_rt_free(pl->d_bsnr);

@@ -48,6 +48,14 @@ SB_DEVICE float4 sb_ld_stream(const float4* p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// read-twice-soon data (the sibling row group of the same CTA wants the other half of every
+// sector): keep it in L1, but first in line for eviction
+SB_DEVICE float4 sb_ld_shared_soon(const float4* p) {
+    float4 r;
+    asm("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 // hint: pull one 128-byte line towards L2 ahead of the loads that will need it
 SB_DEVICE void sb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // a / b to ~2 ulp (MUFU.RCP + multiply); used where the tolerance is 1e-4

@@ -162,24 +162,19 @@ class Plan(object):
         angles = np.asarray(angles, dtype=np.float64)
         A, G = len(angles), len(ages)
         lo, hi = (0, A) if angle_slice is None else angle_slice
-        arr_a = (SbAngle * max(hi - lo, 1))()
-        arr_t = (SbTemplate * max((hi - lo) * G, 1))()
+        ai, gi = np.meshgrid(np.arange(A), np.arange(G), indexing="ij")
+        idx = gi * A + ai if order == "age_major" else ai * G + gi          # [A, G]
         age_of = np.empty(A * G, dtype=np.float64)
         angle_of = np.empty(A * G, dtype=np.float64)
-        for ai in range(A):
-            for gi in range(G):
-                idx = gi * A + ai if order == "age_major" else ai * G + gi
-                age_of[idx] = ages[gi]
-                angle_of[idx] = angles[ai]
-        n = 0
-        for k, ai in enumerate(range(lo, hi)):
-            ang = angles[ai]
-            arr_a[k] = P.angle_record(ang)
-            for gi in range(G):
-                idx = gi * A + ai if order == "age_major" else ai * G + gi
-                arr_t[n] = P.template_record(spec, scale, ages[gi], ang, self.nx, self.ny,
-                                             self.dx, self.x, self.y, k, idx)
-                n += 1
+        age_of[idx] = ages[gi]
+        angle_of[idx] = angles[ai]
+        arr_a = (SbAngle * max(hi - lo, 1))()
+        for k, a in enumerate(range(lo, hi)):
+            arr_a[k] = P.angle_record(angles[a])
+        recs = P.template_records(spec, scale, ages, angles[lo:hi], self.nx, self.ny, self.dx,
+                                  self.x, self.y, np.arange(hi - lo), idx[lo:hi])
+        arr_t = P.records_to_ctypes(recs)
+        n = (hi - lo) * G
         return (arr_a, hi - lo), (arr_t, n), age_of, angle_of
 
     def reset(self):

@@ -122,6 +122,101 @@ class DeviceSpec(object):
         self.edge_mask = edge_mask
 
 
+def _age_scalars(spec, age, nx, de):
+    """(c, k0, k1, c_eff, tscale) of one age: everything in ``template_record`` that does
+    not depend on the orientation."""
+    if spec.kind == KIND_SCARP:
+        kt = age
+        c = float(scarp_halfwidth(kt))
+        k0 = float(2. * kt ** (3 / 2.) * np.sqrt(np.pi))   # WindowedTemplate.py:177
+        k1 = float(4. * kt)                                # :178
+        c_eff = c
+    elif spec.kind == KIND_RICKER:
+        f = age
+        c = float(nx)                                      # WindowedTemplate.py:491
+        k0 = float(np.pi * f)                              # :514
+        k1 = 0.0
+        c_eff = c
+        if abs(k0) > 0:
+            c_eff = min(c, np.sqrt(_EXP_UNDERFLOW) / abs(k0) + abs(de))
+    else:
+        raise ValueError("unknown template kind %r" % (spec.kind,))
+    return c, k0, k1, c_eff, packing_scale(spec.kind, k0, k1, c_eff)
+
+
+TEMPLATE_DTYPE = np.dtype([(name, np.float64 if ctype is SbTemplate._fields_[0][1] else np.int32)
+                           for name, ctype in SbTemplate._fields_], align=True)
+
+
+def template_records(spec, scale, ages, angles, nx, ny, de, x, y, angle_ids, idx):
+    """All ``SbTemplate`` records of the fan-out ``angles`` x ``ages`` at once: a structured
+    array of shape (len(angles), len(ages)), field for field what ``template_record``
+    returns (tests/test_host_logic.py holds the two against each other).  The reference
+    evaluates the trigonometry on scalars (WindowedTemplate.py:57, 68-75), so it is done per
+    angle here too; the rest is IEEE arithmetic in the reference's operation order,
+    vectorised.  ``angle_ids`` [A] and ``idx`` [A, G] are copied into the records."""
+    ages = np.asarray(ages, dtype=np.float64)
+    angles = np.asarray(angles, dtype=np.float64)
+    A, G = len(angles), len(ages)
+    if A == 0 or G == 0 or not (np.all(np.diff(x) > 0) and np.all(np.diff(y) > 0)):
+        out = np.zeros((A, G), dtype=TEMPLATE_DTYPE)
+        for a in range(A):
+            for g in range(G):
+                rec = template_record(spec, scale, ages[g], angles[a], nx, ny, de, x, y,
+                                      angle_ids[a], idx[a][g])
+                out[a, g] = tuple(getattr(rec, name) for name, _ in SbTemplate._fields_)
+        return out
+    alpha = [-float(a) for a in angles]              # WindowedTemplate.py:151, 489
+    ca = np.array([float(np.cos(a)) for a in alpha])[:, None]
+    sa = np.array([float(np.sin(a)) for a in alpha])[:, None]
+    cq = np.array([float(np.cos(a - np.pi / 2)) for a in alpha])[:, None]
+    sq = np.array([float(np.sin(a - np.pi / 2)) for a in alpha])[:, None]
+    d = float(scale)
+    per_age = [_age_scalars(spec, float(age), nx, de) for age in ages]
+    c, k0, k1, c_eff, tscale = (np.array(v, dtype=np.float64)[None, :] for v in zip(*per_age))
+
+    out = np.zeros((A, G), dtype=TEMPLATE_DTYPE)
+    out["cos_t"], out["sin_t"] = ca, sa
+    out["c"], out["d"], out["k0"], out["k1"], out["tscale"] = c, d, k0, k1, tscale
+    out["sign"], out["kind"], out["errmode"] = float(spec.sign), spec.kind, spec.errmode
+    # support_box
+    step = abs(float(de))
+    ex = (c_eff * np.abs(ca) + d * np.abs(sa)) / step
+    ey = (c_eff * np.abs(sa) + d * np.abs(ca)) / step
+    a0, b0 = ny // 2, nx // 2
+    rx = np.minimum(ex, 4.0 * nx).astype(np.int64) + 2
+    ry = np.minimum(ey, 4.0 * ny).astype(np.int64) + 2
+    out["sx_lo"], out["sx_hi"] = np.maximum(-rx, -b0), np.minimum(rx, nx - 1 - b0)
+    out["sy_lo"], out["sy_hi"] = np.maximum(-ry, -a0), np.minimum(ry, ny - 1 - a0)
+    # window_rectangle
+    if spec.edge_mask:
+        x4, y4, x1, y1 = d * cq, d * sq, d * ca, d * sa
+        an_y = np.abs((x4 - x1) + 2 * c * cq)
+        an_x = np.abs((y1 - y4) + 2 * c * sq)
+        # ~((v < lo) | (v > hi)) on a rising axis is the run [first v >= lo, last v <= hi]
+        j_lo = np.searchsorted(x, np.min(x) + an_x, side="left")
+        j_hi = np.searchsorted(x, np.max(x) - an_x, side="right") - 1
+        i_lo = np.searchsorted(y, np.min(y) + an_y, side="left")
+        i_hi = np.searchsorted(y, np.max(y) - an_y, side="right") - 1
+        empty = (j_lo > j_hi) | (i_lo > i_hi)
+        out["i_lo"], out["i_hi"] = np.where(empty, 1, i_lo), np.where(empty, 0, i_hi)
+        out["j_lo"], out["j_hi"] = np.where(empty, 1, j_lo), np.where(empty, 0, j_hi)
+    else:
+        out["i_lo"], out["i_hi"], out["j_lo"], out["j_hi"] = 0, ny - 1, 0, nx - 1
+    out["angle_id"] = np.asarray(angle_ids, dtype=np.int32)[:, None]
+    out["idx"] = np.asarray(idx, dtype=np.int32)
+    return out
+
+
+def records_to_ctypes(records):
+    """Flat ctypes ``SbTemplate`` array (what ``sb_sweep`` takes) from a structured array."""
+    flat = np.ascontiguousarray(records).reshape(-1)
+    arr = (SbTemplate * max(len(flat), 1))()
+    if len(flat):
+        np.frombuffer(arr, dtype=TEMPLATE_DTYPE, count=len(flat))[:] = flat
+    return arr
+
+
 def template_record(spec, scale, age, angle, nx, ny, de, x, y, angle_id, idx):
     """``SbTemplate`` for ``Template(scale, age, angle, nx, ny, de)`` (core.py:345)."""
     alpha = -angle                                   # WindowedTemplate.py:151, 489

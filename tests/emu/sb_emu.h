@@ -157,6 +157,7 @@ template <typename T> SB_DEVICE T sb_ldg(const T* p) { return *p; }
 SB_DEVICE void sb_prefetch_l2(const void*) {}
 SB_DEVICE float2 sb_ld_stream(const float2* p) { return *p; }
 SB_DEVICE float4 sb_ld_stream(const float4* p) { return *p; }
+SB_DEVICE float4 sb_ld_shared_soon(const float4* p) { return *p; }
 SB_DEVICE float sb_fdiv_fast(float a, float b) { return a / b; }
 
 // built with -ffp-contract=off, so these stay separate IEEE operations

@@ -152,3 +152,32 @@ def test_shard_bounds():
         sizes = [hi - lo for lo, hi in cuts]
         assert max(sizes) - min(sizes) <= 1
     assert [shard_bounds(181, 8, r)[1] - shard_bounds(181, 8, r)[0] for r in range(8)] == [23] * 5 + [22] * 3
+
+
+@pytest.mark.parametrize("ny,nx,de,cls,scale,ages", [
+    (200, 200, 1.0, "Scarp", 100.0, [10.0]),
+    (465, 870, 2.0, "Scarp", 30.0, None),
+    (300, 301, 1.0, "Channel", 10.0, [0.1, 0.02]),
+    (150, 170, 1.0, "RightFacingUpperBreakScarp", 10.0, [2.0, 20.0]),
+    (64, 96, -1.0, "Scarp", 8.0, [2.0]),               # falling axes: per-record fallback
+])
+def test_bulk_template_records_equal_single(ny, nx, de, cls, scale, ages):
+    """The vectorised record builder (one call per sweep) against the per-template one that
+    mirrors the reference expression by expression."""
+    from scarplet_b200 import params as P
+    from scarplet_b200 import templates as T
+    from scarplet_b200._lib import SbTemplate
+    spec = getattr(T, cls)._sb_spec
+    ages = P.default_ages() if ages is None else np.asarray(ages, dtype=np.float64)
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)
+    x, y = P.axis_vectors(nx, ny, de)
+    A, G = len(angles), len(ages)
+    idx = np.arange(G)[None, :] * A + np.arange(A)[:, None]
+    recs = P.template_records(spec, scale, ages, angles, nx, ny, de, x, y, np.arange(A), idx)
+    assert recs.shape == (A, G) and recs.dtype.itemsize == ctypes.sizeof(SbTemplate)
+    for a in range(0, A, 3):
+        for g in range(G):
+            one = P.template_record(spec, scale, ages[g], angles[a], nx, ny, de, x, y, a, idx[a, g])
+            assert tuple(getattr(one, n) for n, _ in SbTemplate._fields_) == tuple(recs[a, g].tolist())
+    arr = P.records_to_ctypes(recs)
+    assert arr[G + 1].idx == idx[1, 1 % G] if G > 1 else arr[1].idx == idx[1, 0]
