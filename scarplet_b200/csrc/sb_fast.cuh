@@ -27,6 +27,15 @@ using std::max;
 using std::min;
 #endif
 
+// Developer ablation switches (scratch/ablate.sh): build with -DSB_ABLATE and set SB_DBG to
+// switch parts of the kernels' memory traffic off and time what is left.  Compiled out of
+// the product build.
+#ifdef SB_ABLATE
+#define SB_DBG_ON(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define SB_DBG_ON(flags, bit) false
+#endif
+
 SB_CONSTEXPR int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 
 // ---------------------------------------------------------------------------
@@ -93,7 +102,7 @@ struct ConvCtx {
     SB_CONSTEXPR static int stage_of(int P) { return P < NST ? P : P - NST + 1; }
 
     template <int P> SB_DEVICE void twid(float2 (&w)[TW]) {
-        if (dbg & 4) {
+        if (SB_DBG_ON(dbg, 4)) {
 #pragma unroll
             for (int i = 0; i < TW; ++i) w[i] = make_float2(0.6f, 0.8f);
             return;
@@ -108,7 +117,7 @@ struct ConvCtx {
             const float2* spec = F == 0 ? specA : specB;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
-                const float2 s = (dbg & 2) ? make_float2(0.5f, 0.25f) : sb_ld_stream(spec + q * T);
+                const float2 s = SB_DBG_ON(dbg, 2) ? make_float2(0.5f, 0.25f) : sb_ld_stream(spec + q * T);
                 const float2 pr = sbfft::cmul(v[q], s);
                 v[q] = make_float2(pr.y, pr.x);                  // swap: inverse via forward
             }
@@ -126,7 +135,7 @@ struct ConvCtx {
                 for (int q = 0; q < E; ++q) {
                     const int io = (t + q * T + dly) & (N - 1);
                     const float2 a = smA[t + q * T];
-                    if ((dbg & 1) && v[q].x != 1.2345e-30f) continue;
+                    if (SB_DBG_ON(dbg, 1) && v[q].x != 1.2345e-30f) continue;
                     if (io < out_ny) dst[gbuf_index(t + q * T, kx, kpitch)] = make_float4(a.y, a.x, v[q].y, v[q].x);
                 }
             }
@@ -184,7 +193,7 @@ k_conv_cols_f(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_ba
         const int qy = t + q * T;
         const int s = qy < N / 2 ? qy : qy - N;
         if (active && s >= sy_lo && s <= sy_hi) {
-            const float4 w = (g.dbg & 8) ? make_float4(1.f, 2.f, 3.f, 4.f) : sb_ld_stream(src + (s - sy_lo));
+            const float4 w = SB_DBG_ON(g.dbg, 8) ? make_float4(1.f, 2.f, 3.f, 4.f) : sb_ld_stream(src + (s - sy_lo));
             va[q] = make_float2(w.x, w.y);
             vb[q] = make_float2(w.z, w.w);
         }
@@ -255,7 +264,7 @@ struct FitCtx {
     }
 
     template <int P> SB_DEVICE void twid(float2 (&w)[TW]) {
-        if (dbg & 32) {
+        if (SB_DBG_ON(dbg, 32)) {
 #pragma unroll
             for (int i = 0; i < TW; ++i) w[i] = make_float2(0.6f, 0.8f);
             return;
@@ -283,7 +292,7 @@ struct FitCtx {
                 int kk = q < E / 2 ? t + q * T : N - (t + q * T);
                 if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
                 // PAIRED: the CTA's other row group reads the other half of each sector
-                if (row) g4 = (dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)q)
+                if (row) g4 = SB_DBG_ON(dbg, 16) ? make_float4(1.f, 2.f, 3.f, (float)q)
                               : PAIRED ? sb_ld_shared_soon(row + 2 * kk) : sb_ld_stream(row + 2 * kk);
                 v[q] = direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
             }
@@ -293,7 +302,7 @@ struct FitCtx {
             if ((F == 0 ? rowA : rowB) != nullptr) {
                 const unsigned slot = F == 0 ? slotA : slotB;
                 const FitT k = s_fit[slot];
-                if ((dbg & 64) && v[0].x != 1.2345e-30f) return;
+                if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
                 const unsigned mk = mask(k);
 #pragma unroll
                 for (int q = 0; q < E; ++q) {

@@ -194,20 +194,31 @@ SB_DEVICE void stage_store(const typename Vec<R>::v2 (&v)[E], int t, typename Ve
     constexpr int RADIX = stage_radix(N, S);
     constexpr int NS = stage_ns(N, S);
     constexpr int B = E / RADIX;
+    // pad_index(base + u*NS) is linear in u (NS is 1 or a multiple of 16): one address per
+    // butterfly, the rest are immediate offsets
+    static_assert(NS == 1 || NS % 16 == 0, "stage_store: unexpected stage geometry");
+    constexpr int STEP = NS == 1 ? 1 : NS + NS / 16;
 #pragma unroll
     for (int m = 0; m < B; ++m) {
         const int j = t + m * T;
         const int base = (j / NS) * (NS * RADIX) + (j & (NS - 1));
+        typename Vec<R>::v2* p = sm + pad_index(base);
 #pragma unroll
-        for (int u = 0; u < RADIX; ++u) sm[pad_index(base + u * NS)] = v[m + u * B];
+        for (int u = 0; u < RADIX; ++u) p[u * STEP] = v[m + u * B];
     }
 }
 
 template <int N, typename R>
 SB_DEVICE void stage_load(typename Vec<R>::v2 (&v)[E], int t, const typename Vec<R>::v2* sm) {
     constexpr int T = N / E;
+    if constexpr (T % 16 == 0) {
+        const typename Vec<R>::v2* p = sm + pad_index(t);     // pad_index(t + q*T) = pad_index(t) + q*(T + T/16)
 #pragma unroll
-    for (int q = 0; q < E; ++q) v[q] = sm[pad_index(t + q * T)];
+        for (int q = 0; q < E; ++q) v[q] = p[q * (T + T / 16)];
+    } else {
+#pragma unroll
+        for (int q = 0; q < E; ++q) v[q] = sm[pad_index(t + q * T)];
+    }
 }
 
 // First stage (radix 16, no twiddles) when only v[0] and v[15] are non-zero: the
