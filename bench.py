@@ -314,15 +314,23 @@ def run_ours(args):
     dom_ms, dom_launches = prof.get(dom, (0.0, 0))
     my_evals = n * n * len(ages) * (hi - lo) * args.steps       # rank 0's share
     achieved = ALGO_BYTES[dom] * my_evals / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # DRAM bytes of the same kernel from the committed `ncu --set full` capture
+    # (profiles/traffic.json, bytes per px-eval) scaled to this run's average launch
     traffic = None
+    traffic_src = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f).get(dom)
+        if tj and dom_launches:
+            traffic = tj["dram_bytes_per_px_eval"] * my_evals / dom_launches
+            traffic_src = tj.get("source")
     except Exception:
         pass
     total_kernel_ms = sum(v[0] for v in prof.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                "achieved_bytes_per_launch": (ALGO_BYTES[dom] * my_evals / dom_launches) if dom_launches else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_px_eval": ALGO_BYTES[dom],
                 "avg_launch_ms": dom_ms / dom_launches if dom_launches else None,
                 "launches": dom_launches,

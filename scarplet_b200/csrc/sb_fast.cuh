@@ -44,6 +44,7 @@ SB_CONSTEXPR int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 //   phase<P, F>(v,w) register work of the phase
 //   store<P, F>(v)   scatter to the stream's exchange buffer (not after the last phase)
 //   load<F>(v)       gather the next phase's elements
+//   bar()            barrier over the threads that carry the two transforms
 // On entry to Frog<P>: a has finished phase P and stored it, a barrier has passed,
 // b holds its phase-P input in vb (and wb).
 // ---------------------------------------------------------------------------
@@ -55,12 +56,12 @@ struct Frog {
             c.template store<P, 1>(vb);
             c.template load<0>(va);
             c.template twid<P + 1>(wa);
-            sb_sync();
+            c.bar();
             c.template phase<P + 1, 0>(va, wa);
             if constexpr (P + 1 < K - 1) c.template store<P + 1, 0>(va);
             c.template load<1>(vb);
             c.template twid<P + 1>(wb);
-            if constexpr (P + 1 < K - 1) sb_sync();
+            if constexpr (P + 1 < K - 1) c.bar();
             Frog<P + 1, K, Ctx>::run(c, va, vb, wa, wb);
         }
     }
@@ -73,7 +74,7 @@ SB_DEVICE void leapfrog(Ctx& c, float2 (&va)[E], float2 (&vb)[E]) {
     c.template twid<0>(wb);
     c.template phase<0, 0>(va, wa);
     c.template store<0, 0>(va);
-    sb_sync();
+    c.bar();
     Frog<0, K, Ctx>::run(c, va, vb, wa, wb);
 }
 
@@ -86,7 +87,9 @@ SB_DEVICE void leapfrog(Ctx& c, float2 (&va)[E], float2 (&vb)[E]) {
 // SPARSE: the template support is shorter than T rows on either side of the origin,
 // so each thread's only non-zero inputs are elements 0 and 15 (stage0_sparse2).
 // ---------------------------------------------------------------------------
-template <int N, bool SPARSE>
+// PERSIST (k_conv_cols_p): the spectrum columns are in shared memory and the thread group has
+// its own named barrier.
+template <int N, bool SPARSE, bool PERSIST = false>
 struct ConvCtx {
     static constexpr int NST = sbfft::num_stages(N);
     static constexpr int K = 2 * NST - 1;
@@ -98,6 +101,12 @@ struct ConvCtx {
     float4* dst;                      // gbuf plane of this template (nullptr: inactive group)
     int kx, dly, out_ny, kpitch;
     int dbg;
+    int bar_id;                       // PERSIST: named barrier of this thread group
+
+    SB_DEVICE void bar() const {
+        if constexpr (PERSIST) sb_bar(bar_id, T);
+        else sb_sync();
+    }
 
     SB_CONSTEXPR static int stage_of(int P) { return P < NST ? P : P - NST + 1; }
 
@@ -117,7 +126,8 @@ struct ConvCtx {
             const float2* spec = F == 0 ? specA : specB;
 #pragma unroll
             for (int q = 0; q < E; ++q) {
-                const float2 s = SB_DBG_ON(dbg, 2) ? make_float2(0.5f, 0.25f) : sb_ld_stream(spec + q * T);
+                const float2 s = SB_DBG_ON(dbg, 2) ? make_float2(0.5f, 0.25f)
+                                 : PERSIST ? spec[q * T] : sb_ld_stream(spec + q * T);
                 const float2 pr = sbfft::cmul(v[q], s);
                 v[q] = make_float2(pr.y, pr.x);                  // swap: inverse via forward
             }
@@ -202,6 +212,101 @@ k_conv_cols_f(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_ba
 }
 
 // ---------------------------------------------------------------------------
+// k_conv_cols_p<Py, SPARSE>: persistent variant, grid (KX), 512 threads = G groups of T.
+// A CTA owns one spectrum column kx for the whole batch of templates.  The batch is
+// walked in runs of templates that share a search angle: the two curvature-spectrum
+// columns of that angle are staged in shared memory ONCE and multiplied into every
+// template of the run (k_conv_cols_f fetches them from L2 per template, right where the
+// product needs them -- a third of its warp stalls); the twiddles stay in registers
+// for the whole batch; the groups take the templates of a run round-robin, each behind
+// its own named barrier.
+// ---------------------------------------------------------------------------
+constexpr int kConvPThreads = 512;
+constexpr int kConvPMaxBatch = 64;
+
+template <int N, bool SPARSE>
+SB_GLOBAL SB_LAUNCH_BOUNDS(kConvPThreads, 1)
+k_conv_cols_p(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int angle_base,
+              const float4* SB_RESTRICT trt, const float2* SB_RESTRICT fct, float4* SB_RESTRICT gbuf,
+              const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    constexpr int G = kConvPThreads / T;
+    constexpr int PL = sbfft::padded_len(N);
+    static_assert(T >= 32 && G >= 1, "k_conv_cols_p: one group must be whole warps");
+    typedef ConvCtx<N, SPARSE, true> Ctx;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    const int KX = g.Px / 2 + 1;
+    const int kx = sb_bx();
+    float2* sm = (float2*)sb_shared();
+    float2* spec_s = sm + (long)G * 2 * PL;               // [2][N]
+    int* s_meta = (int*)(spec_s + 2 * N);                  // [cnt][4]: sy_lo, sy_hi, angle_id
+
+    for (int i = sb_tid(); i < cnt; i += kConvPThreads) {
+        const Tmpl* p = tmpls + tmpl_base + i;
+        s_meta[4 * i + 0] = p->sy_lo;
+        s_meta[4 * i + 1] = p->sy_hi;
+        s_meta[4 * i + 2] = p->angle_id - angle_base;
+    }
+
+    Ctx c;
+    c.t = t;
+    c.smA = sm + (long)grp * 2 * PL;
+    c.smB = c.smA + PL;
+    c.tw = tw;
+    c.specA = spec_s + t;
+    c.specB = spec_s + N + t;
+    c.kx = kx;
+    c.dly = g.dly;
+    c.out_ny = g.out_ny;
+    c.kpitch = g.kpitch;
+    c.dbg = g.dbg;
+    c.bar_id = 1 + grp;
+    sb_sync();
+
+    int s0 = 0;
+#pragma unroll 1
+    while (s0 < cnt) {
+        const int a_loc = s_meta[4 * s0 + 2];
+        int s1 = s0 + 1;
+        while (s1 < cnt && s_meta[4 * s1 + 2] == a_loc) ++s1;
+        if (s0 > 0) sb_sync();                              // the previous run's products are done
+        {
+            const float4* src = (const float4*)(fct + (((long)a_loc * 2) * KX + kx) * N);
+            const float4* src2 = (const float4*)(fct + (((long)a_loc * 2 + 1) * KX + kx) * N);
+            float4* dst = (float4*)spec_s;
+            for (int i = sb_tid(); i < N / 2; i += kConvPThreads) {
+                dst[i] = sb_ld_stream(src + i);
+                dst[N / 2 + i] = sb_ld_stream(src2 + i);
+            }
+        }
+        sb_sync();
+#pragma unroll 1
+        for (int p_loc = s0 + grp; p_loc < s1; p_loc += G) {
+            const int sy_lo = s_meta[4 * p_loc + 0], sy_hi = s_meta[4 * p_loc + 1];
+            const float4* src = trt + ((long)p_loc * KX + kx) * g.syp;
+            c.dst = gbuf + (long)p_loc * N * g.kpitch;
+            float2 va[E], vb[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                va[q] = make_float2(0.f, 0.f);
+                vb[q] = make_float2(0.f, 0.f);
+                if (SPARSE && q != 0 && q != E - 1) continue;
+                const int qy = t + q * T;
+                const int s = qy < N / 2 ? qy : qy - N;
+                if (s >= sy_lo && s <= sy_hi) {
+                    const float4 w = sb_ld_stream(src + (s - sy_lo));
+                    va[q] = make_float2(w.x, w.y);
+                    vb[q] = make_float2(w.z, w.w);
+                }
+            }
+            leapfrog<Ctx::K>(c, va, vb);                    // the last phase of field b writes gbuf
+            c.bar();                                        // parked field a has been read back
+        }
+        s0 = s1;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // k_fit_rows_f<Px>: grid (ceil(out_ny / GP)); every CTA walks the batch of templates
 // two at a time.  Per template and row: Hermitian-extended inverse row FFT of
 // Gt + i Gm (real part xcorr, imaginary part T3), amplitude / SNR (core.py:360-367),
@@ -212,17 +317,18 @@ k_conv_cols_f(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_ba
 // ---------------------------------------------------------------------------
 constexpr int kFitMaxBatch = 64;
 
-SB_DEVICE void fit_pixel_fast(float xraw, float traw, const FitT& k, float& amp, float& snr) {
-    const float x = xraw * k.xn;                     // xcorr  (exact scaling)
-    const float t3 = traw * k.tn;                    // T3     (exact scaling)
-    amp = x * k.its_hi;                              // core.py:360
-    const float pp = x * x;
-    const float pe = fmaf(x, x, -pp);                // x*x = pp + pe exactly
-    float num = fmaf(-pp, k.its_hi, t3);             // T3 - x^2/ts, error-free products
-    num = fmaf(-pp, k.its_lo, num);
-    num = fmaf(-pe, k.its_hi, num);
-    const float t1 = x * amp;                        // core.py:362
-    const float err = fmaf(num, k.inv_n, (float)kEps);   // core.py:366
+// X, T: raw outputs of the inverse transform (xcorr and T3 up to the exact power-of-two
+// factors folded into FitT).  snr = |T1 / error| with error = (T3 - xcorr^2 / ts) / n + eps
+// (core.py:362-367); the cancellation T3 - xcorr^2 / ts is evaluated with error-free products.
+SB_DEVICE void fit_pixel_fast(float X, float T, const FitT& k, float& amp, float& snr) {
+    amp = X * k.amp_k;                               // core.py:360
+    const float pp = X * X;
+    const float pe = fmaf(X, X, -pp);                // X*X = pp + pe exactly
+    float num = fmaf(-pp, k.a_hi, T);
+    num = fmaf(-pp, k.a_lo, num);
+    num = fmaf(-pe, k.a_hi, num);
+    const float t1 = pp * k.a_hi;                    // core.py:362
+    const float err = fmaf(num, k.inv_n, k.eps_k);   // core.py:366
     snr = fabsf(sb_fdiv_fast(t1, err));              // core.py:367
 }
 
@@ -251,9 +357,11 @@ struct FitCtx {
 
     SB_DEVICE FitCtx(float (&s)[E], float (&a)[E], unsigned (&w)[E / 4]) : bs(s), ba(a), bw(w) {}
 
+    SB_DEVICE void bar() const { sb_sync(); }
     SB_DEVICE unsigned slot_of(int q) const { return (bw[q >> 2] >> (8 * (q & 3))) & 0xFFu; }
-    SB_DEVICE void set_slot(int q, unsigned slot) {
-        bw[q >> 2] = (bw[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | (slot << (8 * (q & 3)));
+    // word with byte `b` replaced by `slot`
+    SB_DEVICE static unsigned with_slot(unsigned word, int b, unsigned slot) {
+        return (word & ~(0xFFu << (8 * b))) | (slot << (8 * b));
     }
     // flat index behind the current best of element q (rare path: exact SNR ties only)
     SB_DEVICE int current_idx(int q) const {
@@ -269,7 +377,7 @@ struct FitCtx {
             for (int i = 0; i < TW; ++i) w[i] = make_float2(0.6f, 0.8f);
             return;
         }
-        sbfft::load_tw<N, P, float>(w, t, tw);
+        sbfft::load_tw<N, P, float, true>(w, t, tw);      // tw: the CTA's shared-memory copy
     }
 
     // bit q set <=> column t + q*T of this row lies inside the template's window
@@ -304,19 +412,31 @@ struct FitCtx {
                 const FitT k = s_fit[slot];
                 if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
                 const unsigned mk = mask(k);
+                // first maximum wins (core.py:230-240).  The select is branch-free; equal
+                // positive SNRs (in float32 mostly the -90 / +90 degree pair) are rare and
+                // resolved afterwards to the lower flat index, so that the result does not
+                // depend on the batch order.
+                unsigned ties = 0u;
 #pragma unroll
                 for (int q = 0; q < E; ++q) {
                     float amp, snr;
                     fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
-                    // first maximum wins (core.py:230-240); equal positive SNRs resolve to the
-                    // lower flat index so the result does not depend on batch order
-                    const bool ok = (mk >> q) & 1u;
-                    bool take = ok && snr > bs[q];
-                    if (ok && snr == bs[q] && snr > 0.f) take = k.idx < current_idx(q);
-                    if (take) {
-                        bs[q] = snr;
-                        ba[q] = amp;
-                        set_slot(q, slot);
+                    snr = ((mk >> q) & 1u) ? snr : -1.f;          // edge-masked: never wins
+                    const bool take = snr > bs[q];
+                    ties |= (snr == bs[q] && snr > 0.f) ? (1u << q) : 0u;
+                    bs[q] = take ? snr : bs[q];
+                    ba[q] = take ? amp : ba[q];
+                    bw[q >> 2] = take ? with_slot(bw[q >> 2], q & 3, slot) : bw[q >> 2];
+                }
+                if (ties != 0u) {
+#pragma unroll
+                    for (int q = 0; q < E; ++q) {
+                        if (((ties >> q) & 1u) && k.idx < current_idx(q)) {
+                            float amp, snr;
+                            fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
+                            ba[q] = amp;
+                            bw[q >> 2] = with_slot(bw[q >> 2], q & 3, slot);
+                        }
                     }
                 }
             }
@@ -345,6 +465,10 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
     int* s_list = (int*)(s_fit + kFitMaxBatch);          // [kFitMaxBatch] active templates, then their count
     int* s_flag = s_list + kFitMaxBatch + 1;             // [kFitMaxBatch]
+    // the twiddle table next to the data: 30 table reads per thread and template would
+    // otherwise compete with the streamed planes for L1 and mostly come back from L2
+    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 1);
+    for (int i = sb_tid(); i < sbfft::twiddle_count(N); i += THREADS) tw_s[i] = sb_ldg(tw + i);
     const int io = sb_bx() * GP + grp;
     const bool active = io < g.out_ny;
     const int gi = g.oy + io;
@@ -373,7 +497,7 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     c.t = t;
     c.smA = sm + (long)grp * 2 * PL;
     c.smB = c.smA + PL;
-    c.tw = tw;
+    c.tw = tw_s;
     c.gi = gi;
     c.ox = g.ox;
     c.m0 = t + g.dlx;

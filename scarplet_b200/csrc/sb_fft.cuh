@@ -152,7 +152,8 @@ template <typename R> struct Dft<R, 16> {
 // together for the simple one-transform-at-a-time kernels.
 constexpr int TW = E - 1;    // twiddle registers a thread needs for one stage (at most)
 
-template <int N, int S, typename R>
+// SMEM: `tw` is a copy of the table in shared memory (plain loads)
+template <int N, int S, typename R, bool SMEM = false>
 SB_DEVICE void load_tw(typename Vec<R>::v2 (&w)[TW], int t, const typename Vec<R>::v2* SB_RESTRICT tw) {
     constexpr int T = N / E;
     constexpr int RADIX = stage_radix(N, S);
@@ -164,7 +165,8 @@ SB_DEVICE void load_tw(typename Vec<R>::v2 (&w)[TW], int t, const typename Vec<R
     for (int m = 0; m < B; ++m) {
         const int k = (t + m * T) & (NS - 1);
 #pragma unroll
-        for (int u = 1; u < RADIX; ++u) w[(u - 1) * B + m] = ld2(tw + TWO + (u - 1) * NS + k);
+        for (int u = 1; u < RADIX; ++u)
+            w[(u - 1) * B + m] = SMEM ? tw[TWO + (u - 1) * NS + k] : ld2(tw + TWO + (u - 1) * NS + k);
     }
 }
 

@@ -74,9 +74,13 @@ struct TSum {                // per-template scalars produced by k_tmpl_sums
 constexpr double kEps = 2.220446049250313e-16;   // np.spacing(1), core.py:339
 
 // per-template scalars of the float32 epilogue of k_fit_rows_f (written by k_tmpl_sums)
+// xn = norm / tscale and tn = norm / c2_scale are exact powers of two that undo the packing
+// scales and the unnormalised FFTs; they are folded into the constants below (exactly), so
+// the epilogue works on the raw transform outputs X = xcorr / xn, T = T3 / tn.
 struct FitT {
-    float xn, tn;            // exact powers of two: norm / tscale, norm / c2_scale
-    float its_hi, its_lo;    // 1/ts = hi + lo
+    float amp_k;             // xn / ts                  amp = X * amp_k            core.py:360
+    float a_hi, a_lo;        // xn**2 / (ts * tn) = hi + lo
+    float eps_k;             // eps / tn
     float inv_n;
     int i_lo, i_hi, j_lo, j_hi;   // un-masked output window (core.py:373-375)
     int idx;                 // flat result index
@@ -386,10 +390,13 @@ SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int 
     sums[p_loc] = s;
     if (fit) {
         FitT k;
-        k.xn = (float)(g.norm / p.tscale);
-        k.tn = (float)(g.norm / g.c2_scale);
-        k.its_hi = (float)s.inv_ts;
-        k.its_lo = (float)(s.inv_ts - (double)k.its_hi);
+        const double xn = g.norm / p.tscale, tn = g.norm / g.c2_scale;     // powers of two
+        const float its_hi = (float)s.inv_ts;
+        const float its_lo = (float)(s.inv_ts - (double)its_hi);
+        k.amp_k = (float)((double)its_hi * xn);
+        k.a_hi = (float)((double)its_hi * (xn * xn / tn));
+        k.a_lo = (float)((double)its_lo * (xn * xn / tn));
+        k.eps_k = (float)(kEps / tn);
         k.inv_n = (float)s.inv_n;
         k.i_lo = p.i_lo; k.i_hi = p.i_hi; k.j_lo = p.j_lo; k.j_hi = p.j_hi;
         k.idx = p.idx;

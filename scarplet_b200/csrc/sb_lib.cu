@@ -84,6 +84,7 @@ struct sb_plan {
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
     Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
+    int conv_persist = std::getenv("SB_CONV_P") ? std::atoi(std::getenv("SB_CONV_P")) : 1;
     int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 256;
     long launches = 0;
     double c2_scale = 1.0;
@@ -94,7 +95,7 @@ struct sb_plan {
     size_t ev_used = 0;
     double prof_ms[6] = {0, 0, 0, 0, 0, 0};
     long prof_n[6] = {0, 0, 0, 0, 0, 0};
-    long workspace_mb = 8192;
+    long workspace_mb = 0;         // 0: half of the free device memory, at most 48 GB
     int max_fft = kMaxFftSupported;
     int force_pad = 0;
     int last_geom[6] = {0, 0, 0, 0, 0, 0};
@@ -173,7 +174,8 @@ struct Shape {
     // batch's scalars, the active-template list (+ its length) and the flags
     static constexpr size_t smem_conv_f = (size_t)GP * 2 * sbfft::padded_len(N) * sizeof(float2);
     static constexpr size_t smem_fit_f = smem_conv_f + sb::kFitMaxBatch * sizeof(sb::FitT) +
-                                         (2 * sb::kFitMaxBatch + 1) * sizeof(int);
+                                         (2 * sb::kFitMaxBatch + 2) * sizeof(int) +
+                                         (size_t)sbfft::twiddle_count(N) * sizeof(float2);
 };
 
 #ifndef SB_EMU
@@ -362,7 +364,14 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
     const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)Py * kpitch * sizeof(C4) +
                             (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
-    const size_t budget = (size_t)pl->workspace_mb << 20;
+    size_t budget = (size_t)pl->workspace_mb << 20;
+    if (pl->workspace_mb <= 0) {
+        // auto: the workspace already held counts as free
+        size_t free_b = 0, total_b = 0, held = 0;
+        for (const Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf}) held += b->cap;
+        if (sb_rt_mem_info(&free_b, &total_b) != 0) free_b = (size_t)16 << 30;
+        budget = std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)1 << 30, (free_b + held) / 2));
+    }
     // templates per angle (max) decides the split of the budget
     std::vector<int> first(n_angles + 1, 0);
     for (auto& t : tm) first[t.angle_id + 1]++;
@@ -376,7 +385,9 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     Ba = std::min(Ba, 64);
     if (max_per_angle == 1) Bt = std::min(Bt, Ba), Ba = std::min(Ba, Bt);
     Bt = std::min(Bt, n_tmpls);
-    if (Bt > 1) Bt &= ~1;            // k_fit_rows_f walks the batch two templates at a time
+    // whole angles per batch when they fit: templates of one angle share the curvature spectra
+    if (max_per_angle > 1 && Bt >= max_per_angle) Bt = (Bt / max_per_angle) * max_per_angle;
+    else if (Bt > 1) Bt &= ~1;       // k_fit_rows_f walks the batch two templates at a time
 
     SB_OK(ensure(pl->cr, (size_t)Ba * need_rows_max * kpitch * sizeof(C4)));
     SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(C2)));
@@ -469,6 +480,27 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                 // every template column has at most two non-zero inputs per thread
                                 const bool sparse = hi_y <= S::T - 1 && lo_y >= -S::T;
                                 ProfScope prof(pl, K_CONV_COLS);
+                                if constexpr (N >= 1024 && N <= 4096) {
+                                    if (pl->conv_persist && cnt <= sb::kConvPMaxBatch) {
+                                        constexpr size_t smem_p =
+                                            (size_t)(sb::kConvPThreads / S::T) * 2 * sbfft::padded_len(N) * sizeof(float2) +
+                                            (size_t)2 * N * sizeof(float2) + sb::kConvPMaxBatch * 4 * sizeof(int);
+                                        if (sparse) {
+                                            auto kern = sb::k_conv_cols_p<N, true>;
+                                            SB_ALLOW_SMEM(kern, smem_p);
+                                            SB_LAUNCH(kern, dim3(KX), dim3(sb::kConvPThreads), smem_p, pl->stream, g, d_tm,
+                                                      pb, cnt, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
+                                                      (float4*)pl->gbuf.p, (const float2*)twy);
+                                        } else {
+                                            auto kern = sb::k_conv_cols_p<N, false>;
+                                            SB_ALLOW_SMEM(kern, smem_p);
+                                            SB_LAUNCH(kern, dim3(KX), dim3(sb::kConvPThreads), smem_p, pl->stream, g, d_tm,
+                                                      pb, cnt, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
+                                                      (float4*)pl->gbuf.p, (const float2*)twy);
+                                        }
+                                        return check_launch(pl, "k_conv_cols_p");
+                                    }
+                                }
                                 const dim3 grid(cnt, div_up(KX, S::GP));
                                 if (sparse) {
                                     auto kern = sb::k_conv_cols_f<N, true>;
@@ -641,7 +673,7 @@ int sb_plan_destroy(sb_plan* pl) {
 int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
     if (!pl || !key) return fail("sb_plan_set_option: null");
     std::string k(key);
-    if (k == "workspace_mb") { pl->workspace_mb = std::max(64L, value); return 0; }
+    if (k == "workspace_mb") { pl->workspace_mb = value <= 0 ? 0 : std::max(64L, value); return 0; }
     if (k == "max_fft") {
         if (!is_pow2((int)value) || value < kMinFft || value > kMaxFftSupported)
             return fail("max_fft must be a power of two in [128, 8192]");

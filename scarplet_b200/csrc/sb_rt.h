@@ -31,6 +31,8 @@ SB_DEVICE int sb_by() { return blockIdx.y; }
 SB_DEVICE int sb_bz() { return blockIdx.z; }
 SB_DEVICE int sb_nbx() { return gridDim.x; }
 SB_DEVICE void sb_sync() { __syncthreads(); }
+// named barrier: `count` threads (a multiple of 32) of the block meet at barrier `id` (1..15)
+SB_DEVICE void sb_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 SB_DEVICE void* sb_shared() {
     extern __shared__ __align__(16) unsigned char sb_smem_raw[];
     return sb_smem_raw;
@@ -110,6 +112,7 @@ inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t s) {
     return (int)cudaMemsetAsync(d, v, n, s);
 }
 inline int sb_rt_sync(sb_stream_t s) { return (int)cudaStreamSynchronize(s); }
+inline int sb_rt_mem_info(size_t* free_b, size_t* total_b) { return (int)cudaMemGetInfo(free_b, total_b); }
 inline int sb_rt_last_error() { return (int)cudaGetLastError(); }
 // 3-D float32 tensor map: dims (elements, fastest first), strides in bytes of dims 1 and 2,
 // box (elements).  cuTensorMapEncodeTiled is fetched through the runtime, no -lcuda needed.

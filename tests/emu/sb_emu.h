@@ -45,6 +45,8 @@ struct Fiber {
     char* stack = nullptr;
     int tid = 0;
     bool done = false;
+    int wait_id = -1;      // barrier the fiber is parked at (-1: runnable)
+    int wait_count = 0;    // threads that barrier expects (0: every live thread of the block)
 };
 
 struct Block {
@@ -93,22 +95,44 @@ inline void run_blocks(dim3 grid, int nthreads, size_t smem_bytes,
             Fiber& f = fibers[t];
             f.tid = t;
             f.done = false;
+            f.wait_id = -1;
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = f.stack;
             f.ctx.uc_stack.ss_size = kStack;
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
-        int alive = nthreads;
-        while (alive > 0) {
-            alive = 0;
+        // run every runnable fiber to its next barrier (or to the end), then open the barriers
+        // whose expected number of threads has arrived
+        for (;;) {
+            int alive = 0, ran = 0;
             for (int t = 0; t < nthreads; ++t) {
                 Fiber& f = fibers[t];
                 if (f.done) continue;
+                ++alive;
+                if (f.wait_id >= 0) continue;
                 blk.cur = &f;
-                swapcontext(&blk.sched, &f.ctx);  // runs to the next barrier or to the end
-                if (!f.done) ++alive;
+                swapcontext(&blk.sched, &f.ctx);
+                ++ran;
             }
+            if (alive == 0) break;
+            int live = 0, opened = 0;
+            int waiting[17] = {0};
+            for (int t = 0; t < nthreads; ++t) {
+                Fiber& f = fibers[t];
+                if (f.done) continue;
+                ++live;
+                if (f.wait_id >= 0) ++waiting[f.wait_id];
+            }
+            for (int t = 0; t < nthreads; ++t) {
+                Fiber& f = fibers[t];
+                if (f.done || f.wait_id < 0) continue;
+                const int expect = f.wait_count > 0 ? f.wait_count : live;
+                if (waiting[f.wait_id] >= expect) { f.wait_id = -1 - 100 - f.wait_id; ++opened; }   // mark, open below
+            }
+            for (int t = 0; t < nthreads; ++t)
+                if (!fibers[t].done && fibers[t].wait_id < -1) fibers[t].wait_id = -1;
+            if (ran == 0 && opened == 0) std::abort();     // barrier deadlock in the kernel under test
         }
     }
     current() = nullptr;
@@ -148,10 +172,15 @@ SB_DEVICE int sb_bx() { return sbemu::current()->bx; }
 SB_DEVICE int sb_by() { return sbemu::current()->by; }
 SB_DEVICE int sb_bz() { return sbemu::current()->bz; }
 SB_DEVICE int sb_nbx() { return (int)sbemu::current()->grid.x; }
-SB_DEVICE void sb_sync() {
+// named barrier: `count` threads of the block meet at barrier `id` (1..15); id 0 with count 0
+// is the block-wide barrier over the threads that are still running
+SB_DEVICE void sb_bar(int id, int count) {
     sbemu::Block* b = sbemu::current();
+    b->cur->wait_id = id;
+    b->cur->wait_count = count;
     swapcontext(&b->cur->ctx, &b->sched);
 }
+SB_DEVICE void sb_sync() { sb_bar(0, 0); }
 SB_DEVICE void* sb_shared() { return sbemu::current()->smem; }
 template <typename T> SB_DEVICE T sb_ldg(const T* p) { return *p; }
 SB_DEVICE void sb_prefetch_l2(const void*) {}
@@ -213,6 +242,7 @@ inline int sb_rt_d2h(void* h, const void* d, size_t n, sb_stream_t) { std::memcp
 inline int sb_rt_d2d(void* d, const void* s, size_t n, sb_stream_t) { std::memcpy(d, s, n); return 0; }
 inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t) { std::memset(d, v, n); return 0; }
 inline int sb_rt_sync(sb_stream_t) { return 0; }
+inline int sb_rt_mem_info(size_t* free_b, size_t* total_b) { *free_b = *total_b = (size_t)2 << 30; return 0; }
 inline int sb_rt_last_error() { return 0; }
 typedef int sb_event_t;
 inline int sb_rt_event_create(sb_event_t* e) { *e = 0; return 0; }

@@ -128,3 +128,39 @@ def test_compare_exact_semantics(emu_lib, golden):
     st = [np.stack([r[0], np.full((2, 2), r[1]), np.full((2, 2), r[2]), r[3]]) for r in (r1, r2, r3)]
     out2 = np.stack(sl.compare(st, 2, 2))
     assert np.array_equal(out2, out)
+
+
+@pytest.mark.parametrize("scale,ages", [(10, [2.0, 20.0, 60.0]), (70, [5.0])])
+def test_persistent_column_kernel(emu_lib, scale, ages):
+    """Column FFT length 1024 takes k_conv_cols_p (one CTA per spectrum column, 8 thread
+    groups behind named barriers, curvature-spectrum columns staged in shared memory per
+    run of same-angle templates): runs shorter and longer than the group count, sparse
+    (scale 10) and dense (scale 70 > T = 64 rows) template columns."""
+    from scarplet_b200 import params as P
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.synth import synthetic_dem
+    from scarplet_b200.templates import Scarp
+    import os
+    ny, nx = 1024, 200
+    z = synthetic_dem(ny, seed=21, nx=nx, relief=3.0)
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)[[3, 50, 90, 140]]
+    outs = {}
+    for persist in ("1", "0"):
+        os.environ["SB_CONV_P"] = persist            # read when the plan is created
+        try:
+            with Plan(ny, nx, 1.0, 1.0) as plan:
+                plan.set_dem(z)
+                a, t, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, scale, ages, angles)
+                plan.reset()
+                plan.sweep(a, t)
+                outs[persist] = plan.finalize(age_of, angle_of)
+                assert plan.last_geometry()["Py"] == 1024
+        finally:
+            del os.environ["SB_CONV_P"]
+    # same arithmetic in the same order as the per-template kernel
+    assert np.array_equal(outs["1"], outs["0"])
+    ref = O.compare((O.match_template(z, 1.0, 1.0, O.SCARP, scale, age, ang)
+                     for age in ages for ang in angles), ny, nx)
+    rep = stack_report(outs["1"], np.stack(ref))
+    assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.999, rep
+    assert rep["snr_rel_p50"] < 1e-5 and rep["frac_snr_over_tol"] <= 2e-2, rep
