@@ -107,7 +107,6 @@ struct ConvCtx {
         if constexpr (PERSIST) sb_bar(bar_id, T);
         else sb_sync();
     }
-
     SB_CONSTEXPR static int stage_of(int P) { return P < NST ? P : P - NST + 1; }
 
     template <int P> SB_DEVICE void twid(float2 (&w)[TW]) {
@@ -555,6 +554,202 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
             best_amp[o] = ba[q];
             best_idx[o] = s_fit[slot].idx;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k_fit_rows_g<Px>: row-pair variant of k_fit_rows_f; grid (Py / 2 / GP).  The two transforms
+// a thread group pipelines are the two raster rows that share every 32-byte sector of the
+// interleaved planes (gbuf_index), of ONE template: a thread fetches whole sectors with
+// 256-bit loads and feeds one half to each row, so the planes cross the L2 -> SM crossbar
+// in full sectors (k_fit_rows_f used 16 bytes of every 32 it requested: 4x the algorithmic
+// traffic together with the Hermitian re-read, which here hits L1).  The running best keeps
+// only the SNR in registers; amplitude and flat index go straight to the best state when a
+// pixel improves (rare after the first templates of a sweep).
+// ---------------------------------------------------------------------------
+template <int N>
+struct FitPairCtx {
+    static constexpr int K = sbfft::num_stages(N);
+    static constexpr int T = N / E;
+    static constexpr int LOG2T = ilog2(T);
+    int t;
+    float2 *smA, *smB;
+    const float2* tw;
+    const float4* pair;               // the template's row pair: element kk of row F at pair[2 * kk + F]
+    const FitT* s_fit;
+    int slot;
+    int giA, giB;                     // raster rows of the two streams
+    bool actA, actB;
+    int ox, m0, out_nx, nx;
+    float* best_amp;
+    int* best_idx;
+    float (&bsA)[E];
+    float (&bsB)[E];
+    float2 (&vb_in)[E];               // stream b's input, filled together with stream a's
+    unsigned chg;                     // bit q (+16 for row B): the pixel's best SNR changed
+
+    SB_DEVICE FitPairCtx(float (&a)[E], float (&b)[E], float2 (&vb)[E]) : bsA(a), bsB(b), vb_in(vb), chg(0u) {}
+
+    SB_DEVICE void bar() const { sb_sync(); }
+
+    template <int P> SB_DEVICE void twid(float2 (&w)[TW]) { sbfft::load_tw<N, P, float, true>(w, t, tw); }
+
+    SB_DEVICE unsigned mask(const FitT& k, int gi, bool act) const {
+        if (!act || gi < k.i_lo || gi > k.i_hi) return 0u;
+        const int lo = max(k.j_lo - ox, 0), hi = min(k.j_hi - ox, out_nx - 1);
+        const int qlo = max((lo - m0 + T - 1) >> LOG2T, 0);
+        const int qhi = min((hi - m0) >> LOG2T, E - 1);
+        return qlo <= qhi ? ((2u << qhi) - (1u << qlo)) : 0u;
+    }
+
+    // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped (inverse via forward)
+    SB_DEVICE static float2 herm(const float4 g4, bool direct) {
+        return direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
+    }
+
+    template <int F> SB_DEVICE void epilogue(const float2 (&v)[E], float (&bs)[E]) {
+        const int gi = F == 0 ? giA : giB;
+        const FitT k = s_fit[slot];
+        const unsigned mk = mask(k, gi, F == 0 ? actA : actB);
+        float* pa = best_amp + ((long)gi * nx + ox);
+        int* pi = best_idx + ((long)gi * nx + ox);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            float amp, snr;
+            fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
+            snr = ((mk >> q) & 1u) ? snr : -1.f;              // edge-masked: never wins
+            // first maximum wins (core.py:230-240); equal positive SNRs (in float32 mostly the
+            // -90 / +90 degree pair) go to the lower flat index, whatever the batch order.
+            // (A branch-free select over the 16 pixels was measured 3 % slower: it spills.)
+            if (snr >= bs[q] && snr > 0.f) {
+                const int jo = (m0 + q * T) & (N - 1);
+                if (snr > bs[q] || k.idx < pi[jo]) {
+                    bs[q] = snr;
+                    pa[jo] = amp;
+                    pi[jo] = k.idx;
+                    chg |= 1u << (q + 16 * F);
+                }
+            }
+        }
+    }
+
+    template <int P, int F> SB_DEVICE void phase(float2 (&v)[E], const float2 (&w)[TW]) {
+        if constexpr (P == 0 && F == 0) {
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                bool direct = q < E / 2;
+                int kk = q < E / 2 ? t + q * T : N - (t + q * T);
+                if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
+                float4 ga, gb;
+                sb_ld_sector(pair + 2 * kk, ga, gb);
+                v[q] = herm(ga, direct);
+                vb_in[q] = herm(gb, direct);
+            }
+        }
+        sbfft::stage_math<N, P, float>(v, w);
+        if constexpr (P == K - 1) {
+            if constexpr (F == 0) epilogue<0>(v, bsA);
+            else epilogue<1>(v, bsB);
+        }
+    }
+    template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
+        sbfft::stage_store<N, P, float>(v, t, F == 0 ? smA : smB);
+    }
+    template <int F> SB_DEVICE void load(float2 (&v)[E]) { sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB); }
+};
+
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RESTRICT gbuf,
+             float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
+             const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    constexpr int THREADS = T > 256 ? T : 256;
+    constexpr int GP = THREADS / T;
+    constexpr int PL = sbfft::padded_len(N);
+    typedef FitPairCtx<N> Ctx;
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    float2* sm = (float2*)sb_shared();
+    FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
+    int* s_list = (int*)(s_fit + kFitMaxBatch);          // [kFitMaxBatch] active templates, then their count
+    int* s_flag = s_list + kFitMaxBatch + 1;             // [kFitMaxBatch]
+    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 1);
+    for (int i = sb_tid(); i < sbfft::twiddle_count(N); i += THREADS) tw_s[i] = sb_ldg(tw + i);
+    const int pairs = g.Py / 2;
+    const int pr = min(sb_bx() * GP + grp, pairs - 1);    // row pair of the FFT domain
+    const int ioA = (2 * pr + g.dly) & (g.Py - 1), ioB = (2 * pr + 1 + g.dly) & (g.Py - 1);
+    const bool actA = sb_bx() * GP + grp < pairs && ioA < g.out_ny;
+    const bool actB = sb_bx() * GP + grp < pairs && ioB < g.out_ny;
+
+    // stage the batch's scalars; list the templates whose window meets one of this CTA's rows
+    if (sb_tid() < count) {
+        const FitT k = fit[sb_tid()];
+        s_fit[sb_tid()] = k;
+        int flag = 0;
+        for (int r = 0; r < 2 * GP; ++r) {
+            const int m = 2 * sb_bx() * GP + r;
+            const int io = (m + g.dly) & (g.Py - 1);
+            if (m < g.Py && io < g.out_ny && g.oy + io >= k.i_lo && g.oy + io <= k.i_hi) flag = 1;
+        }
+        s_flag[sb_tid()] = flag;
+    }
+    sb_sync();
+    if (sb_tid() < count) {
+        int pos = 0;
+        for (int i = 0; i < sb_tid(); ++i) pos += s_flag[i];
+        if (s_flag[sb_tid()]) s_list[pos] = sb_tid();
+        if (sb_tid() == count - 1) s_list[kFitMaxBatch] = pos + s_flag[sb_tid()];
+    }
+    sb_sync();
+    const int n_act = s_list[kFitMaxBatch];
+
+    float bsA[E], bsB[E];
+    float2 va[E], vb[E];
+    Ctx c(bsA, bsB, vb);
+    c.t = t;
+    c.smA = sm + (long)grp * 2 * PL;
+    c.smB = c.smA + PL;
+    c.tw = tw_s;
+    c.giA = g.oy + ioA;
+    c.giB = g.oy + ioB;
+    c.actA = actA;
+    c.actB = actB;
+    c.ox = g.ox;
+    c.m0 = t + g.dlx;
+    c.out_nx = g.out_nx;
+    c.nx = g.nx;
+    c.s_fit = s_fit;
+    c.best_amp = best_amp;
+    c.best_idx = best_idx;
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int jo = (t + q * T + g.dlx) & (N - 1);
+        const bool in = jo < g.out_nx;
+        bsA[q] = (actA && in) ? best_snr[(long)c.giA * g.nx + g.ox + jo] : 0.f;
+        bsB[q] = (actB && in) ? best_snr[(long)c.giB * g.nx + g.ox + jo] : 0.f;
+    }
+    const long row_off = gbuf_index(2 * pr, 0, g.kpitch);
+    const long tmpl_pitch = (long)g.Py * g.kpitch;
+    const int lines = (2 * (g.Px / 2 + 1) + 7) / 8;        // 128-byte lines of one row pair
+
+#pragma unroll 1
+    for (int i = 0; i < n_act; ++i) {
+        const int p = s_list[i];
+        c.pair = gbuf + p * tmpl_pitch + row_off;
+        c.slot = p;
+        if (i + 1 < n_act) {                                // next template's row pair towards L2
+            const float4* nx0 = gbuf + s_list[i + 1] * tmpl_pitch + row_off;
+            for (int l = t; l < lines; l += T) sb_prefetch_l2(nx0 + 8 * l);
+        }
+        // no barrier between templates: buffer A was last read before the final barrier,
+        // buffer B is next written after the coming template's first barrier
+        leapfrog<Ctx::K>(c, va, vb);
+    }
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int jo = (t + q * T + g.dlx) & (N - 1);
+        if ((c.chg >> q) & 1u) best_snr[(long)c.giA * g.nx + g.ox + jo] = bsA[q];
+        if ((c.chg >> (q + 16)) & 1u) best_snr[(long)c.giB * g.nx + g.ox + jo] = bsB[q];
     }
 }
 

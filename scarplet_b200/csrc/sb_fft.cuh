@@ -74,6 +74,35 @@ template <typename C> SB_DEVICE C cmul(C a, C b) {
 }
 template <typename C> SB_DEVICE C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }   // a * (-i)
 
+// ---- packed FP32 (sm_100a FADD2 / FMUL2 / FFMA2) -------------------------------
+// A float2 is one 64-bit register pair; add/mul/fma.f32x2 work on both halves in one issue
+// slot, and ptxas folds half swaps, per-half negations and scalar broadcasts of the operands
+// into the instruction (R.F32x2.LO_HI, .NP, R.F32), so a complex add is 1 instruction
+// instead of 2, a complex multiply 2 instead of 4, and multiplying by -i is free.  The
+// butterflies below are written against these helpers; the emulator build and complex128
+// use the scalar forms above.
+#if !defined(SB_EMU) && !defined(SB_NO_F32X2)
+#define SB_F32X2 1
+typedef unsigned long long pk_t;
+SB_DEVICE pk_t pk(float lo, float hi) { pk_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+SB_DEVICE pk_t pk(float2 a) { return pk(a.x, a.y); }
+SB_DEVICE float2 unpk(pk_t v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+SB_DEVICE pk_t add2(pk_t a, pk_t b) { pk_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+SB_DEVICE pk_t mul2(pk_t a, pk_t b) { pk_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+SB_DEVICE pk_t fma2(pk_t a, pk_t b, pk_t c) { pk_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+SB_DEVICE float2 cadd(float2 a, float2 b) { return unpk(add2(pk(a), pk(b))); }
+SB_DEVICE float2 csub(float2 a, float2 b) { return unpk(add2(pk(a), pk(-b.x, -b.y))); }
+SB_DEVICE float2 cmul(float2 a, float2 b) {
+    return unpk(fma2(pk(-a.y, a.x), pk(b.y, b.y), mul2(pk(a), pk(b.x, b.x))));
+}
+// e + s * r, e - s * r for a real scalar r
+SB_DEVICE float2 caxpy(float2 e, float2 s, float r) { return unpk(fma2(pk(s), pk(r, r), pk(e))); }
+// a - i a = (a.x + a.y, a.y - a.x);  -(a + i a) = (a.y - a.x, -a.x - a.y)
+SB_DEVICE float2 rot_m45(float2 a) { return unpk(add2(pk(a), pk(a.y, -a.x))); }
+SB_DEVICE float2 rot_m135(float2 a) { return unpk(add2(pk(a.y, -a.x), pk(-a.x, -a.y))); }
+#endif
+
 template <typename R, int RADIX> struct Dft;
 
 template <typename R> struct Dft<R, 2> {
@@ -144,6 +173,53 @@ template <typename R> struct Dft<R, 16> {
     }
 };
 
+#ifdef SB_F32X2
+// float specialisations: the W8 / W16 constant rotations fold into packed FMAs
+template <> struct Dft<float, 8> {
+    typedef float2 C;
+    SB_DEVICE static void run(C* x) {
+        const float h = 0.70710678118654752440f;
+        C e[4] = {x[0], x[2], x[4], x[6]};
+        C o[4] = {x[1], x[3], x[5], x[7]};
+        Dft<float, 4>::run(e);
+        Dft<float, 4>::run(o);
+        const C s1 = rot_m45(o[1]), s3 = rot_m135(o[3]), s2 = mul_mi(o[2]);
+        x[0] = cadd(e[0], o[0]);  x[4] = csub(e[0], o[0]);
+        x[1] = caxpy(e[1], s1, h);  x[5] = caxpy(e[1], s1, -h);
+        x[2] = cadd(e[2], s2);  x[6] = csub(e[2], s2);
+        x[3] = caxpy(e[3], s3, h);  x[7] = caxpy(e[3], s3, -h);
+    }
+};
+
+template <> struct Dft<float, 16> {
+    typedef float2 C;
+    SB_DEVICE static void run(C* x) {
+        const float h = 0.70710678118654752440f;
+        const float c1 = 0.92387953251128675613f;   // cos(pi/8)
+        const float s1 = 0.38268343236508977173f;   // sin(pi/8)
+        C e[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
+        Dft<float, 8>::run(e);
+        Dft<float, 8>::run(o);
+        // o[k] *= W16^k = exp(-i*pi*k/8); the multiples of pi/4 fold into the final add
+        o[1] = cmul(o[1], make_float2(c1, -s1));
+        o[3] = cmul(o[3], make_float2(s1, -c1));
+        o[5] = cmul(o[5], make_float2(-s1, -c1));
+        o[7] = cmul(o[7], make_float2(-c1, -s1));
+        const C r2 = rot_m45(o[2]), r6 = rot_m135(o[6]), r4 = mul_mi(o[4]);
+        x[0] = cadd(e[0], o[0]);  x[8] = csub(e[0], o[0]);
+        x[1] = cadd(e[1], o[1]);  x[9] = csub(e[1], o[1]);
+        x[2] = caxpy(e[2], r2, h);  x[10] = caxpy(e[2], r2, -h);
+        x[3] = cadd(e[3], o[3]);  x[11] = csub(e[3], o[3]);
+        x[4] = cadd(e[4], r4);  x[12] = csub(e[4], r4);
+        x[5] = cadd(e[5], o[5]);  x[13] = csub(e[5], o[5]);
+        x[6] = caxpy(e[6], r6, h);  x[14] = caxpy(e[6], r6, -h);
+        x[7] = cadd(e[7], o[7]);  x[15] = csub(e[7], o[7]);
+    }
+};
+#endif
+
 // ---- one Stockham stage, split into its four parts ----------------------------
 // v[q] = x[t + q*T].  A stage is: fetch the thread's twiddles (global, L1-resident),
 // multiply + radix butterflies in registers, scatter to the exchange buffer in the
@@ -153,6 +229,19 @@ template <typename R> struct Dft<R, 16> {
 constexpr int TW = E - 1;    // twiddle registers a thread needs for one stage (at most)
 
 // SMEM: `tw` is a copy of the table in shared memory (plain loads)
+// Twiddle diet (complex64, radix 16): only W^k, W^2k, W^3k, W^4k, W^8k, W^12k are fetched; the
+// other nine are one complex product of two of those (1.5 ulp instead of 0.5).  The table
+// reads of a stage drop from 15 to 6 per thread -- they share the LSU with the exchange --
+// and 18 fewer registers are live across the barrier that follows the fetch.
+template <typename R, int RADIX>
+SB_CONSTEXPR bool tw_derived(int u) {
+#if defined(SB_F32X2) && !defined(SB_NO_TW_DIET)
+    return sizeof(R) == 4 && RADIX == 16 && !(u <= 4 || u == 8 || u == 12);
+#else
+    return false;
+#endif
+}
+
 template <int N, int S, typename R, bool SMEM = false>
 SB_DEVICE void load_tw(typename Vec<R>::v2 (&w)[TW], int t, const typename Vec<R>::v2* SB_RESTRICT tw) {
     constexpr int T = N / E;
@@ -165,8 +254,10 @@ SB_DEVICE void load_tw(typename Vec<R>::v2 (&w)[TW], int t, const typename Vec<R
     for (int m = 0; m < B; ++m) {
         const int k = (t + m * T) & (NS - 1);
 #pragma unroll
-        for (int u = 1; u < RADIX; ++u)
+        for (int u = 1; u < RADIX; ++u) {
+            if (tw_derived<R, RADIX>(u)) continue;          // stage_math multiplies it together
             w[(u - 1) * B + m] = SMEM ? tw[TWO + (u - 1) * NS + k] : ld2(tw + TWO + (u - 1) * NS + k);
+        }
     }
 }
 
@@ -182,7 +273,14 @@ SB_DEVICE void stage_math(typename Vec<R>::v2 (&v)[E], const typename Vec<R>::v2
         for (int u = 0; u < RADIX; ++u) x[u] = v[m + u * B];
         if (S > 0) {
 #pragma unroll
-            for (int u = 1; u < RADIX; ++u) x[u] = cmul(x[u], w[(u - 1) * B + m]);
+            for (int u = 1; u < RADIX; ++u) {
+                if (tw_derived<R, RADIX>(u)) {
+                    const int hi = u & ~3, lo = u & 3;       // u = hi + lo, hi in {4, 8, 12}
+                    x[u] = cmul(x[u], cmul(w[(hi - 1) * B + m], w[(lo - 1) * B + m]));
+                } else {
+                    x[u] = cmul(x[u], w[(u - 1) * B + m]);
+                }
+            }
         }
         Dft<R, RADIX>::run(x);
 #pragma unroll

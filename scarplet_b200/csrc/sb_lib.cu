@@ -85,7 +85,7 @@ struct sb_plan {
     Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     int conv_persist = std::getenv("SB_CONV_P") ? std::atoi(std::getenv("SB_CONV_P")) : 1;
-    int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 256;
+    int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 0;
     long launches = 0;
     double c2_scale = 1.0;
     int profile = 0;
@@ -150,6 +150,10 @@ int twiddles(sb_plan* pl, int n, const typename Vec<R>::v2** out) {
 
 template <typename F>
 int dispatch_n(int n, F&& f) {
+#ifdef SB_DEV_N   // developer builds (scratch/devbuild.sh): one FFT length, a tenth of the compile time
+    if (n == SB_DEV_N) return f(std::integral_constant<int, SB_DEV_N>{});
+    return fail("developer build: only FFT length " + std::to_string(SB_DEV_N));
+#else
     switch (n) {
         case 128: return f(std::integral_constant<int, 128>{});
         case 256: return f(std::integral_constant<int, 256>{});
@@ -160,6 +164,7 @@ int dispatch_n(int n, F&& f) {
         case 8192: return f(std::integral_constant<int, 8192>{});
         default: return fail("unsupported FFT length " + std::to_string(n));
     }
+#endif
 }
 
 template <int N, typename R>
@@ -523,6 +528,15 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                 constexpr int N = decltype(nn)::value;
                                 using S = Shape<N, float>;
                                 ProfScope prof(pl, K_FIT_ROWS);
+                                if (pl->fit_threads == 0) {
+                                    auto kern = sb::k_fit_rows_g<N>;
+                                    SB_ALLOW_SMEM(kern, S::smem_fit_f);
+                                    SB_LAUNCH(kern, dim3(div_up(Py / 2, S::GP)), dim3(S::threads), S::smem_fit_f,
+                                              pl->stream, g, cnt, (const sb::FitT*)pl->fit.p,
+                                              (const float4*)pl->gbuf.p, pl->d_bsnr, pl->d_bamp, pl->d_bidx,
+                                              (const float2*)twx);
+                                    return check_launch(pl, "k_fit_rows_g");
+                                }
                                 if (S::T <= 256 && pl->fit_threads == 512) {
                                     constexpr int threads = S::T > 512 ? S::T : 512;
                                     constexpr int GP = threads / S::T;

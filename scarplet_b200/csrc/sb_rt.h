@@ -33,6 +33,8 @@ SB_DEVICE int sb_nbx() { return gridDim.x; }
 SB_DEVICE void sb_sync() { __syncthreads(); }
 // named barrier: `count` threads (a multiple of 32) of the block meet at barrier `id` (1..15)
 SB_DEVICE void sb_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// signal named barrier `id` without waiting (the `count` includes the threads that will wait)
+SB_DEVICE void sb_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 SB_DEVICE void* sb_shared() {
     extern __shared__ __align__(16) unsigned char sb_smem_raw[];
     return sb_smem_raw;
@@ -57,6 +59,15 @@ SB_DEVICE float4 sb_ld_shared_soon(const float4* p) {
     asm("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];"
         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+}
+// one whole 32-byte sector (two adjacent float4) in one request; kept in L1 until its second
+// reader (the thread that needs the mirrored element) has had it, first in line for eviction
+SB_DEVICE void sb_ld_sector(const float4* p, float4& a, float4& b) {
+#ifndef SB_SECTOR_POLICY
+#define SB_SECTOR_POLICY ".L1::evict_first"
+#endif
+    asm("ld.global.nc" SB_SECTOR_POLICY ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 // hint: pull one 128-byte line towards L2 ahead of the loads that will need it
 SB_DEVICE void sb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

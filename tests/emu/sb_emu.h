@@ -56,6 +56,7 @@ struct Block {
     ucontext_t sched;
     Fiber* cur = nullptr;
     const std::function<void()>* fn = nullptr;
+    int arrived[17] = {0};   // bar.arrive counts per named barrier (threads that signalled and went on)
 };
 
 inline Block*& current() {
@@ -91,6 +92,7 @@ inline void run_blocks(dim3 grid, int nthreads, size_t smem_bytes,
         blk.by = (int)((b / grid.x) % grid.y);
         blk.bz = (int)(b / ((long)grid.x * grid.y));
         std::memset(smem, 0xCD, smem_bytes);  // poison: shared memory is uninitialised
+        std::memset(blk.arrived, 0, sizeof(blk.arrived));
         for (int t = 0; t < nthreads; ++t) {
             Fiber& f = fibers[t];
             f.tid = t;
@@ -124,12 +126,17 @@ inline void run_blocks(dim3 grid, int nthreads, size_t smem_bytes,
                 ++live;
                 if (f.wait_id >= 0) ++waiting[f.wait_id];
             }
+            int used[17] = {0};
             for (int t = 0; t < nthreads; ++t) {
                 Fiber& f = fibers[t];
                 if (f.done || f.wait_id < 0) continue;
                 const int expect = f.wait_count > 0 ? f.wait_count : live;
-                if (waiting[f.wait_id] >= expect) { f.wait_id = -1 - 100 - f.wait_id; ++opened; }   // mark, open below
+                if (waiting[f.wait_id] + blk.arrived[f.wait_id] >= expect) {
+                    used[f.wait_id] = expect - waiting[f.wait_id];      // arrivals this phase consumed
+                    f.wait_id = -1 - 100 - f.wait_id; ++opened;   // mark, open below
+                }
             }
+            for (int i = 0; i < 17; ++i) blk.arrived[i] -= used[i] > 0 ? used[i] : 0;
             for (int t = 0; t < nthreads; ++t)
                 if (!fibers[t].done && fibers[t].wait_id < -1) fibers[t].wait_id = -1;
             if (ran == 0 && opened == 0) std::abort();     // barrier deadlock in the kernel under test
@@ -180,6 +187,8 @@ SB_DEVICE void sb_bar(int id, int count) {
     b->cur->wait_count = count;
     swapcontext(&b->cur->ctx, &b->sched);
 }
+// bar.arrive: signal barrier `id` and carry on
+SB_DEVICE void sb_bar_arrive(int id, int) { sbemu::current()->arrived[id]++; }
 SB_DEVICE void sb_sync() { sb_bar(0, 0); }
 SB_DEVICE void* sb_shared() { return sbemu::current()->smem; }
 template <typename T> SB_DEVICE T sb_ldg(const T* p) { return *p; }
@@ -187,6 +196,7 @@ SB_DEVICE void sb_prefetch_l2(const void*) {}
 SB_DEVICE float2 sb_ld_stream(const float2* p) { return *p; }
 SB_DEVICE float4 sb_ld_stream(const float4* p) { return *p; }
 SB_DEVICE float4 sb_ld_shared_soon(const float4* p) { return *p; }
+SB_DEVICE void sb_ld_sector(const float4* p, float4& a, float4& b) { a = p[0]; b = p[1]; }
 SB_DEVICE float sb_fdiv_fast(float a, float b) { return a / b; }
 
 // built with -ffp-contract=off, so these stay separate IEEE operations
