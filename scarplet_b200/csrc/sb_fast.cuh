@@ -104,6 +104,9 @@ struct ConvCtx {
     int bar_id;                       // PERSIST: named barrier of this thread group
 
     SB_DEVICE void bar() const {
+#ifdef SB_ABL_NOBAR
+        return;
+#endif
         if constexpr (PERSIST) sb_bar(bar_id, T);
         else sb_sync();
     }
@@ -115,7 +118,7 @@ struct ConvCtx {
             for (int i = 0; i < TW; ++i) w[i] = make_float2(0.6f, 0.8f);
             return;
         }
-        sbfft::load_tw<N, stage_of(P), float>(w, t, tw);
+        sbfft::load_tw<N, stage_of(P), float, PERSIST>(w, t, tw);   // PERSIST: the CTA's shared-memory copy
     }
 
     template <int P, int F> SB_DEVICE void phase(float2 (&v)[E], const float2 (&w)[TW]) {
@@ -145,16 +148,24 @@ struct ConvCtx {
                     const int io = (t + q * T + dly) & (N - 1);
                     const float2 a = smA[t + q * T];
                     if (SB_DBG_ON(dbg, 1) && v[q].x != 1.2345e-30f) continue;
-                    if (io < out_ny) dst[gbuf_index(t + q * T, kx, kpitch)] = make_float4(a.y, a.x, v[q].y, v[q].x);
+                    if (io < out_ny) sb_st_stream(dst + gbuf_index(t + q * T, kx, kpitch), make_float4(a.y, a.x, v[q].y, v[q].x));
                 }
             }
         }
     }
     template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
         constexpr int S = (P == NST - 1) ? 0 : stage_of(P);
+#ifdef SB_ABL_NOXCHG
+        if (v[0].x != 1.2345e-30f) return;
+#endif
         sbfft::stage_store<N, S, float>(v, t, F == 0 ? smA : smB);
     }
-    template <int F> SB_DEVICE void load(float2 (&v)[E]) { sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB); }
+    template <int F> SB_DEVICE void load(float2 (&v)[E]) {
+#ifdef SB_ABL_NOXCHG
+        if (t >= 0) return;
+#endif
+        sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB);
+    }
 };
 
 template <int N, bool SPARSE>
@@ -238,7 +249,9 @@ k_conv_cols_p(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int
     const int kx = sb_bx();
     float2* sm = (float2*)sb_shared();
     float2* spec_s = sm + (long)G * 2 * PL;               // [2][N]
-    int* s_meta = (int*)(spec_s + 2 * N);                  // [cnt][4]: sy_lo, sy_hi, angle_id
+    int* s_meta = (int*)(spec_s + 2 * N);                  // [kConvPMaxBatch][4]: sy_lo, sy_hi, angle_id
+    float2* tw_s = (float2*)(s_meta + 4 * kConvPMaxBatch);  // compact twiddle table
+    sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), kConvPThreads);
 
     for (int i = sb_tid(); i < cnt; i += kConvPThreads) {
         const Tmpl* p = tmpls + tmpl_base + i;
@@ -251,7 +264,7 @@ k_conv_cols_p(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int
     c.t = t;
     c.smA = sm + (long)grp * 2 * PL;
     c.smB = c.smA + PL;
-    c.tw = tw;
+    c.tw = tw_s;
     c.specA = spec_s + t;
     c.specB = spec_s + N + t;
     c.kx = kx;
@@ -279,23 +292,45 @@ k_conv_cols_p(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int
             }
         }
         sb_sync();
-#pragma unroll 1
-        for (int p_loc = s0 + grp; p_loc < s1; p_loc += G) {
+        // SPARSE: a thread's only inputs are rows t and t - T of the template column; they are
+        // fetched one template ahead, so that their latency hides behind the transform
+        float4 in_lo = make_float4(0.f, 0.f, 0.f, 0.f), in_hi = in_lo;
+        auto fetch_sparse = [&](int p_loc) {
             const int sy_lo = s_meta[4 * p_loc + 0], sy_hi = s_meta[4 * p_loc + 1];
             const float4* src = trt + ((long)p_loc * KX + kx) * g.syp;
+            in_lo = make_float4(0.f, 0.f, 0.f, 0.f);
+            in_hi = in_lo;
+            if (t >= sy_lo && t <= sy_hi) in_lo = sb_ld_stream(src + (t - sy_lo));
+            if (t - T >= sy_lo && t - T <= sy_hi) in_hi = sb_ld_stream(src + (t - T - sy_lo));
+        };
+        if (SPARSE && s0 + grp < s1) fetch_sparse(s0 + grp);
+#pragma unroll 1
+        for (int p_loc = s0 + grp; p_loc < s1; p_loc += G) {
             c.dst = gbuf + (long)p_loc * N * g.kpitch;
             float2 va[E], vb[E];
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 va[q] = make_float2(0.f, 0.f);
                 vb[q] = make_float2(0.f, 0.f);
-                if (SPARSE && q != 0 && q != E - 1) continue;
-                const int qy = t + q * T;
-                const int s = qy < N / 2 ? qy : qy - N;
-                if (s >= sy_lo && s <= sy_hi) {
-                    const float4 w = sb_ld_stream(src + (s - sy_lo));
-                    va[q] = make_float2(w.x, w.y);
-                    vb[q] = make_float2(w.z, w.w);
+            }
+            if (SPARSE) {
+                va[0] = make_float2(in_lo.x, in_lo.y);
+                vb[0] = make_float2(in_lo.z, in_lo.w);
+                va[E - 1] = make_float2(in_hi.x, in_hi.y);
+                vb[E - 1] = make_float2(in_hi.z, in_hi.w);
+                if (p_loc + G < s1) fetch_sparse(p_loc + G);
+            } else {
+                const int sy_lo = s_meta[4 * p_loc + 0], sy_hi = s_meta[4 * p_loc + 1];
+                const float4* src = trt + ((long)p_loc * KX + kx) * g.syp;
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    const int qy = t + q * T;
+                    const int s = qy < N / 2 ? qy : qy - N;
+                    if (s >= sy_lo && s <= sy_hi) {
+                        const float4 w = sb_ld_stream(src + (s - sy_lo));
+                        va[q] = make_float2(w.x, w.y);
+                        vb[q] = make_float2(w.z, w.w);
+                    }
                 }
             }
             leapfrog<Ctx::K>(c, va, vb);                    // the last phase of field b writes gbuf
@@ -467,7 +502,7 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     // the twiddle table next to the data: 30 table reads per thread and template would
     // otherwise compete with the streamed planes for L1 and mostly come back from L2
     float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 1);
-    for (int i = sb_tid(); i < sbfft::twiddle_count(N); i += THREADS) tw_s[i] = sb_ldg(tw + i);
+    sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), THREADS);
     const int io = sb_bx() * GP + grp;
     const bool active = io < g.out_ny;
     const int gi = g.oy + io;
@@ -583,6 +618,7 @@ struct FitPairCtx {
     int ox, m0, out_nx, nx;
     float* best_amp;
     int* best_idx;
+    int dbg;
     float (&bsA)[E];
     float (&bsB)[E];
     float2 (&vb_in)[E];               // stream b's input, filled together with stream a's
@@ -633,6 +669,63 @@ struct FitPairCtx {
         }
     }
 
+#ifdef SB_F32X2
+    // Two pixels (q, q + 8) per packed instruction: X = xcorr pair, Tp = T3 pair (fit_pixel_fast).
+    // The window mask is applied to the candidate bits, not to the 16 values; improvements
+    // (rare after the first templates of a sweep) are resolved after the common path.
+    static constexpr bool SOA = sbfft::stage_radix(N, K - 1) == 16 && K > 1;
+    template <int F> SB_DEVICE void epilogue2(const sbfft::pk_t (&re)[8], const sbfft::pk_t (&im)[8], float (&bs)[E]) {
+        using namespace sbfft;
+        const int gi = F == 0 ? giA : giB;
+        const FitT k = s_fit[slot];
+        const unsigned mk = mask(k, gi, F == 0 ? actA : actB);
+        float2 snr2[8], amp2[8];
+        unsigned cand = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const pk_t X = im[j], Tp = re[j];
+            amp2[j] = unpk(mul2(X, pk(k.amp_k, k.amp_k)));                    // core.py:360
+            const pk_t pp = mul2(X, X);
+            const float2 ppf = unpk(pp);
+            const pk_t npp = pk(-ppf.x, -ppf.y);
+            const float2 pef = unpk(fma2(X, X, npp));                          // X*X = pp + pe exactly
+            pk_t num = fma2(npp, pk(k.a_hi, k.a_hi), Tp);
+            num = fma2(npp, pk(k.a_lo, k.a_lo), num);
+            num = fma2(pk(-pef.x, -pef.y), pk(k.a_hi, k.a_hi), num);
+            const float2 t1 = unpk(mul2(pp, pk(k.a_hi, k.a_hi)));              // core.py:362
+            const float2 err = unpk(fma2(num, pk(k.inv_n, k.inv_n), pk(k.eps_k, k.eps_k)));   // core.py:366
+            const float s_lo = fabsf(sb_fdiv_fast(t1.x, err.x));               // core.py:367
+            const float s_hi = fabsf(sb_fdiv_fast(t1.y, err.y));
+            snr2[j] = make_float2(s_lo, s_hi);
+            cand |= (s_lo >= bs[j] && s_lo > 0.f) ? (1u << j) : 0u;
+            cand |= (s_hi >= bs[j + 8] && s_hi > 0.f) ? (1u << (j + 8)) : 0u;
+        }
+        cand &= mk;                                                            // edge-masked: never wins
+        if (cand != 0u) {
+            float* pa = best_amp + ((long)gi * nx + ox);
+            int* pi = best_idx + ((long)gi * nx + ox);
+            // first maximum wins (core.py:230-240); equal positive SNRs (in float32 mostly the
+            // -90 / +90 degree pair) go to the lower flat index, whatever the batch order
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                if ((cand >> q) & 1u) {
+                    const float snr = q < 8 ? snr2[q & 7].x : snr2[q & 7].y;
+                    const float amp = q < 8 ? amp2[q & 7].x : amp2[q & 7].y;
+                    const int jo = (m0 + q * T) & (N - 1);
+                    if (snr > bs[q] || k.idx < pi[jo]) {
+                        bs[q] = snr;
+                        pa[jo] = amp;
+                        pi[jo] = k.idx;
+                        chg |= 1u << (q + 16 * F);
+                    }
+                }
+            }
+        }
+    }
+#else
+    static constexpr bool SOA = false;
+#endif
+
     template <int P, int F> SB_DEVICE void phase(float2 (&v)[E], const float2 (&w)[TW]) {
         if constexpr (P == 0 && F == 0) {
 #pragma unroll
@@ -641,13 +734,25 @@ struct FitPairCtx {
                 int kk = q < E / 2 ? t + q * T : N - (t + q * T);
                 if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
                 float4 ga, gb;
-                sb_ld_sector(pair + 2 * kk, ga, gb);
+                if (SB_DBG_ON(dbg, 16)) { ga = make_float4(1.f, 2.f, 3.f, (float)q); gb = ga; }
+                else sb_ld_sector(pair + 2 * kk, ga, gb);
                 v[q] = herm(ga, direct);
                 vb_in[q] = herm(gb, direct);
             }
         }
+#ifdef SB_F32X2
+        if constexpr (P == K - 1 && SOA) {
+            sbfft::pk_t re[8], im[8];
+            sbfft::stage_math_soa<N, P>(v, w, re, im);
+            if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
+            if constexpr (F == 0) epilogue2<0>(re, im, bsA);
+            else epilogue2<1>(re, im, bsB);
+            return;
+        }
+#endif
         sbfft::stage_math<N, P, float>(v, w);
         if constexpr (P == K - 1) {
+            if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
             if constexpr (F == 0) epilogue<0>(v, bsA);
             else epilogue<1>(v, bsB);
         }
@@ -674,7 +779,7 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     int* s_list = (int*)(s_fit + kFitMaxBatch);          // [kFitMaxBatch] active templates, then their count
     int* s_flag = s_list + kFitMaxBatch + 1;             // [kFitMaxBatch]
     float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 1);
-    for (int i = sb_tid(); i < sbfft::twiddle_count(N); i += THREADS) tw_s[i] = sb_ldg(tw + i);
+    sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), THREADS);
     const int pairs = g.Py / 2;
     const int pr = min(sb_bx() * GP + grp, pairs - 1);    // row pair of the FFT domain
     const int ioA = (2 * pr + g.dly) & (g.Py - 1), ioB = (2 * pr + 1 + g.dly) & (g.Py - 1);
@@ -719,6 +824,7 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     c.out_nx = g.out_nx;
     c.nx = g.nx;
     c.s_fit = s_fit;
+    c.dbg = g.dbg;
     c.best_amp = best_amp;
     c.best_idx = best_idx;
 #pragma unroll

@@ -217,6 +217,33 @@ template <> struct Dft<float, 16> {
         x[6] = caxpy(e[6], r6, h);  x[14] = caxpy(e[6], r6, -h);
         x[7] = cadd(e[7], o[7]);  x[15] = csub(e[7], o[7]);
     }
+    // Same transform, outputs as pairs over (k, k + 8): re[k] = (Re x[k], Re x[k + 8]),
+    // im[k] likewise -- the form a packed two-pixel epilogue wants.  The last butterfly
+    // level e +- s is one FFMA2 per pair with both scalars broadcast: s * (1, -1) + e.
+    SB_DEVICE static void run_soa(C* x, pk_t (&re)[8], pk_t (&im)[8]) {
+        const float h = 0.70710678118654752440f;
+        const float c1 = 0.92387953251128675613f;
+        const float s1 = 0.38268343236508977173f;
+        C e[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
+        Dft<float, 8>::run(e);
+        Dft<float, 8>::run(o);
+        o[1] = cmul(o[1], make_float2(c1, -s1));
+        o[3] = cmul(o[3], make_float2(s1, -c1));
+        o[5] = cmul(o[5], make_float2(-s1, -c1));
+        o[7] = cmul(o[7], make_float2(-c1, -s1));
+        o[2] = rot_m45(o[2]);
+        o[6] = rot_m135(o[6]);
+        o[4] = mul_mi(o[4]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float f = (k == 2 || k == 6) ? h : 1.f;
+            const pk_t pm = pk(f, -f);
+            re[k] = fma2(pk(o[k].x, o[k].x), pm, pk(e[k].x, e[k].x));
+            im[k] = fma2(pk(o[k].y, o[k].y), pm, pk(e[k].y, e[k].y));
+        }
+    }
 };
 #endif
 
@@ -228,7 +255,7 @@ template <> struct Dft<float, 16> {
 // together for the simple one-transform-at-a-time kernels.
 constexpr int TW = E - 1;    // twiddle registers a thread needs for one stage (at most)
 
-// SMEM: `tw` is a copy of the table in shared memory (plain loads)
+// SMEM: `tw` is the compact copy of the table in shared memory (copy_ctw; plain loads)
 // Twiddle diet (complex64, radix 16): only W^k, W^2k, W^3k, W^4k, W^8k, W^12k are fetched; the
 // other nine are one complex product of two of those (1.5 ulp instead of 0.5).  The table
 // reads of a stage drop from 15 to 6 per thread -- they share the LSU with the exchange --
@@ -240,6 +267,45 @@ SB_CONSTEXPR bool tw_derived(int u) {
 #else
     return false;
 #endif
+}
+
+// Compact copy of the table for shared memory: per stage only the rows that are fetched
+// (6 of 15 under the diet), same [row][k] order.
+template <typename R>
+SB_CONSTEXPR int ctw_rows(int N, int s) {
+    const int r = stage_radix(N, s);
+    int n = 0;
+    for (int u = 1; u < r; ++u) n += (r == 16 ? tw_derived<R, 16>(u) : false) ? 0 : 1;
+    return n;
+}
+template <typename R>
+SB_CONSTEXPR int ctw_offset(int N, int s) {
+    int off = 0;
+    for (int i = 1; i < s; ++i) off += ctw_rows<R>(N, i) * stage_ns(N, i);
+    return off;
+}
+template <typename R> SB_CONSTEXPR int ctw_count(int N) { return ctw_offset<R>(N, num_stages(N)); }
+// row of multiplier u in the compact table of a radix-RADIX stage
+template <typename R, int RADIX>
+SB_CONSTEXPR int ctw_row(int u) {
+    int row = 0;
+    for (int i = 1; i < u; ++i) row += tw_derived<R, RADIX>(i) ? 0 : 1;
+    return row;
+}
+// all `nthreads` threads of the CTA: dst (shared) <- compact copy of the table `src` (global)
+template <int N, typename R>
+SB_DEVICE void copy_ctw(typename Vec<R>::v2* dst, const typename Vec<R>::v2* SB_RESTRICT src, int tid, int nthreads) {
+#pragma unroll
+    for (int s = 1; s < num_stages(N); ++s) {
+        const int ns = stage_ns(N, s), r = stage_radix(N, s);
+        int row = 0;
+        for (int u = 1; u < r; ++u) {
+            if (r == 16 && tw_derived<R, 16>(u)) continue;
+            for (int k = tid; k < ns; k += nthreads)
+                dst[ctw_offset<R>(N, s) + row * ns + k] = sb_ldg(src + twiddle_offset(N, s) + (u - 1) * ns + k);
+            ++row;
+        }
+    }
 }
 
 template <int N, int S, typename R, bool SMEM = false>
@@ -256,7 +322,8 @@ SB_DEVICE void load_tw(typename Vec<R>::v2 (&w)[TW], int t, const typename Vec<R
 #pragma unroll
         for (int u = 1; u < RADIX; ++u) {
             if (tw_derived<R, RADIX>(u)) continue;          // stage_math multiplies it together
-            w[(u - 1) * B + m] = SMEM ? tw[TWO + (u - 1) * NS + k] : ld2(tw + TWO + (u - 1) * NS + k);
+            w[(u - 1) * B + m] = SMEM ? tw[ctw_offset<R>(N, S) + ctw_row<R, RADIX>(u) * NS + k]
+                                      : ld2(tw + TWO + (u - 1) * NS + k);
         }
     }
 }
@@ -266,6 +333,9 @@ SB_DEVICE void stage_math(typename Vec<R>::v2 (&v)[E], const typename Vec<R>::v2
     typedef typename Vec<R>::v2 C;
     constexpr int RADIX = stage_radix(N, S);
     constexpr int B = E / RADIX;
+#ifdef SB_ABL_NOMATH
+    if (v[0].x != 1.2345e-30f) return;
+#endif
 #pragma unroll
     for (int m = 0; m < B; ++m) {
         C x[RADIX];
@@ -287,6 +357,26 @@ SB_DEVICE void stage_math(typename Vec<R>::v2 (&v)[E], const typename Vec<R>::v2
         for (int u = 0; u < RADIX; ++u) v[m + u * B] = x[u];
     }
 }
+
+#ifdef SB_F32X2
+// last stage of a transform whose last radix is 16: twiddles + Dft16 with paired outputs
+template <int N, int S>
+SB_DEVICE void stage_math_soa(const float2 (&v)[E], const float2 (&w)[TW], pk_t (&re)[8], pk_t (&im)[8]) {
+    static_assert(stage_radix(N, S) == 16 && S > 0, "stage_math_soa: radix-16 stage expected");
+    float2 x[16];
+    x[0] = v[0];
+#pragma unroll
+    for (int u = 1; u < 16; ++u) {
+        if (tw_derived<float, 16>(u)) {
+            const int hi = u & ~3, lo = u & 3;
+            x[u] = cmul(v[u], cmul(w[hi - 1], w[lo - 1]));
+        } else {
+            x[u] = cmul(v[u], w[u - 1]);
+        }
+    }
+    Dft<float, 16>::run_soa(x, re, im);
+}
+#endif
 
 template <int N, int S, typename R>
 SB_DEVICE void stage_store(const typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm) {

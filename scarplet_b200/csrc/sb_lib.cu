@@ -180,7 +180,7 @@ struct Shape {
     static constexpr size_t smem_conv_f = (size_t)GP * 2 * sbfft::padded_len(N) * sizeof(float2);
     static constexpr size_t smem_fit_f = smem_conv_f + sb::kFitMaxBatch * sizeof(sb::FitT) +
                                          (2 * sb::kFitMaxBatch + 2) * sizeof(int) +
-                                         (size_t)sbfft::twiddle_count(N) * sizeof(float2);
+                                         (size_t)sbfft::ctw_count<float>(N) * sizeof(float2);
 };
 
 #ifndef SB_EMU
@@ -489,7 +489,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                     if (pl->conv_persist && cnt <= sb::kConvPMaxBatch) {
                                         constexpr size_t smem_p =
                                             (size_t)(sb::kConvPThreads / S::T) * 2 * sbfft::padded_len(N) * sizeof(float2) +
-                                            (size_t)2 * N * sizeof(float2) + sb::kConvPMaxBatch * 4 * sizeof(int);
+                                            (size_t)2 * N * sizeof(float2) + sb::kConvPMaxBatch * 4 * sizeof(int) +
+                                            (size_t)sbfft::ctw_count<float>(N) * sizeof(float2);
                                         if (sparse) {
                                             auto kern = sb::k_conv_cols_p<N, true>;
                                             SB_ALLOW_SMEM(kern, smem_p);

@@ -60,6 +60,13 @@ SB_DEVICE float4 sb_ld_shared_soon(const float4* p) {
         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// write-once data (the planes handed to the next kernel)
+#ifndef SB_ST_POLICY
+#define SB_ST_POLICY ".L1::no_allocate"
+#endif
+SB_DEVICE void sb_st_stream(float4* p, float4 v) {
+    asm volatile("st.global" SB_ST_POLICY ".v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // one whole 32-byte sector (two adjacent float4) in one request; kept in L1 until its second
 // reader (the thread that needs the mirrored element) has had it, first in line for eviction
 SB_DEVICE void sb_ld_sector(const float4* p, float4& a, float4& b) {

@@ -196,6 +196,7 @@ SB_DEVICE void sb_prefetch_l2(const void*) {}
 SB_DEVICE float2 sb_ld_stream(const float2* p) { return *p; }
 SB_DEVICE float4 sb_ld_stream(const float4* p) { return *p; }
 SB_DEVICE float4 sb_ld_shared_soon(const float4* p) { return *p; }
+SB_DEVICE void sb_st_stream(float4* p, float4 v) { *p = v; }
 SB_DEVICE void sb_ld_sector(const float4* p, float4& a, float4& b) { a = p[0]; b = p[1]; }
 SB_DEVICE float sb_fdiv_fast(float a, float b) { return a / b; }
 
