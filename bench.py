@@ -279,7 +279,8 @@ def run_ours(args):
                                    device=device, finalize=(rank == 0))
             return out
 
-        e2e_step()
+        for _ in range(3):          # untimed: the plan's page-locked result pool fills (engine._result_array)
+            out = e2e_step()
         fence()
         t0 = time.perf_counter()
         out = None

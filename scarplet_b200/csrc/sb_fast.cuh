@@ -148,6 +148,10 @@ struct ConvCtx {
                     const int io = (t + q * T + dly) & (N - 1);
                     const float2 a = smA[t + q * T];
                     if (SB_DBG_ON(dbg, 1) && v[q].x != 1.2345e-30f) continue;
+                    if (SB_DBG_ON(dbg, 128)) {      // timing only: same bytes, fully coalesced
+                        sb_st_stream(dst + ((long)kx * N + t + q * T), make_float4(a.y, a.x, v[q].y, v[q].x));
+                        continue;
+                    }
                     if (io < out_ny) sb_st_stream(dst + gbuf_index(t + q * T, kx, kpitch), make_float4(a.y, a.x, v[q].y, v[q].x));
                 }
             }
@@ -435,7 +439,7 @@ struct FitCtx {
                 if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
                 // PAIRED: the CTA's other row group reads the other half of each sector
                 if (row) g4 = SB_DBG_ON(dbg, 16) ? make_float4(1.f, 2.f, 3.f, (float)q)
-                              : PAIRED ? sb_ld_shared_soon(row + 2 * kk) : sb_ld_stream(row + 2 * kk);
+                              : PAIRED ? sb_ld_shared_soon(row + kGbufRows * kk) : sb_ld_stream(row + kGbufRows * kk);
                 v[q] = direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
             }
         }
@@ -673,7 +677,7 @@ struct FitPairCtx {
     // Two pixels (q, q + 8) per packed instruction: X = xcorr pair, Tp = T3 pair (fit_pixel_fast).
     // The window mask is applied to the candidate bits, not to the 16 values; improvements
     // (rare after the first templates of a sweep) are resolved after the common path.
-    static constexpr bool SOA = sbfft::stage_radix(N, K - 1) == 16 && K > 1;
+    static constexpr bool SOA = K > 1;
     template <int F> SB_DEVICE void epilogue2(const sbfft::pk_t (&re)[8], const sbfft::pk_t (&im)[8], float (&bs)[E]) {
         using namespace sbfft;
         const int gi = F == 0 ? giA : giB;
@@ -735,7 +739,7 @@ struct FitPairCtx {
                 if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
                 float4 ga, gb;
                 if (SB_DBG_ON(dbg, 16)) { ga = make_float4(1.f, 2.f, 3.f, (float)q); gb = ga; }
-                else sb_ld_sector(pair + 2 * kk, ga, gb);
+                else sb_ld_sector(pair + kGbufRows * kk, ga, gb);
                 v[q] = herm(ga, direct);
                 vb_in[q] = herm(gb, direct);
             }
@@ -836,7 +840,10 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     }
     const long row_off = gbuf_index(2 * pr, 0, g.kpitch);
     const long tmpl_pitch = (long)g.Py * g.kpitch;
-    const int lines = (2 * (g.Px / 2 + 1) + 7) / 8;        // 128-byte lines of one row pair
+    // 128-byte lines that hold the row pair (with kGbufRows > 2 they are shared with the
+    // neighbouring pairs, whose CTAs run at the same time)
+    const int lines = (kGbufRows * (g.Px / 2 + 1) + 7) / 8;
+    const long pf_off = gbuf_index(2 * pr - (2 * pr) % kGbufRows, 0, g.kpitch);
 
 #pragma unroll 1
     for (int i = 0; i < n_act; ++i) {
@@ -844,7 +851,7 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
         c.pair = gbuf + p * tmpl_pitch + row_off;
         c.slot = p;
         if (i + 1 < n_act) {                                // next template's row pair towards L2
-            const float4* nx0 = gbuf + s_list[i + 1] * tmpl_pitch + row_off;
+            const float4* nx0 = gbuf + s_list[i + 1] * tmpl_pitch + pf_off;
             for (int l = t; l < lines; l += T) sb_prefetch_l2(nx0 + 8 * l);
         }
         // no barrier between templates: buffer A was last read before the final barrier,

@@ -220,7 +220,7 @@ template <> struct Dft<float, 16> {
     // Same transform, outputs as pairs over (k, k + 8): re[k] = (Re x[k], Re x[k + 8]),
     // im[k] likewise -- the form a packed two-pixel epilogue wants.  The last butterfly
     // level e +- s is one FFMA2 per pair with both scalars broadcast: s * (1, -1) + e.
-    SB_DEVICE static void run_soa(C* x, pk_t (&re)[8], pk_t (&im)[8]) {
+    SB_DEVICE static void run_soa(C* x, pk_t* re, pk_t* im) {
         const float h = 0.70710678118654752440f;
         const float c1 = 0.92387953251128675613f;
         const float s1 = 0.38268343236508977173f;
@@ -359,22 +359,67 @@ SB_DEVICE void stage_math(typename Vec<R>::v2 (&v)[E], const typename Vec<R>::v2
 }
 
 #ifdef SB_F32X2
-// last stage of a transform whose last radix is 16: twiddles + Dft16 with paired outputs
+// Small DFTs with paired outputs: re[k] = (Re X[k], Re X[k + R/2]), im[k] likewise.  The last
+// butterfly level e +- f*s is one FFMA2 per pair with both scalars broadcast.
+SB_DEVICE void soa_pair(float2 e, float2 s, float f, pk_t& re, pk_t& im) {
+    const pk_t pm = pk(f, -f);
+    re = fma2(pk(s.x, s.x), pm, pk(e.x, e.x));
+    im = fma2(pk(s.y, s.y), pm, pk(e.y, e.y));
+}
+template <int RADIX> struct DftSoa;
+template <> struct DftSoa<2> {
+    SB_DEVICE static void run(float2* x, pk_t* re, pk_t* im) { soa_pair(x[0], x[1], 1.f, re[0], im[0]); }
+};
+template <> struct DftSoa<4> {
+    SB_DEVICE static void run(float2* x, pk_t* re, pk_t* im) {
+        const float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+        const float2 t2 = cadd(x[1], x[3]), t3 = mul_mi(csub(x[1], x[3]));
+        soa_pair(t0, t2, 1.f, re[0], im[0]);
+        soa_pair(t1, t3, 1.f, re[1], im[1]);
+    }
+};
+template <> struct DftSoa<8> {
+    SB_DEVICE static void run(float2* x, pk_t* re, pk_t* im) {
+        const float h = 0.70710678118654752440f;
+        float2 e[4] = {x[0], x[2], x[4], x[6]};
+        float2 o[4] = {x[1], x[3], x[5], x[7]};
+        Dft<float, 4>::run(e);
+        Dft<float, 4>::run(o);
+        soa_pair(e[0], o[0], 1.f, re[0], im[0]);
+        soa_pair(e[1], rot_m45(o[1]), h, re[1], im[1]);
+        soa_pair(e[2], mul_mi(o[2]), 1.f, re[2], im[2]);
+        soa_pair(e[3], rot_m135(o[3]), h, re[3], im[3]);
+    }
+};
+template <> struct DftSoa<16> {
+    SB_DEVICE static void run(float2* x, pk_t* re, pk_t* im) { Dft<float, 16>::run_soa(x, re, im); }
+};
+
+// Last stage of a transform (S > 0) with its outputs paired over (q, q + 8), q = 0..7 -- the
+// form the packed two-pixel epilogue of the fit kernel wants.
 template <int N, int S>
 SB_DEVICE void stage_math_soa(const float2 (&v)[E], const float2 (&w)[TW], pk_t (&re)[8], pk_t (&im)[8]) {
-    static_assert(stage_radix(N, S) == 16 && S > 0, "stage_math_soa: radix-16 stage expected");
-    float2 x[16];
-    x[0] = v[0];
+    constexpr int RADIX = stage_radix(N, S);
+    constexpr int B = E / RADIX;
+    static_assert(S > 0, "stage_math_soa: twiddled stage expected");
 #pragma unroll
-    for (int u = 1; u < 16; ++u) {
-        if (tw_derived<float, 16>(u)) {
-            const int hi = u & ~3, lo = u & 3;
-            x[u] = cmul(v[u], cmul(w[hi - 1], w[lo - 1]));
-        } else {
-            x[u] = cmul(v[u], w[u - 1]);
+    for (int m = 0; m < B; ++m) {
+        float2 x[RADIX];
+        x[0] = v[m];
+#pragma unroll
+        for (int u = 1; u < RADIX; ++u) {
+            if (tw_derived<float, RADIX>(u)) {
+                const int hi = u & ~3, lo = u & 3;
+                x[u] = cmul(v[m + u * B], cmul(w[(hi - 1) * B + m], w[(lo - 1) * B + m]));
+            } else {
+                x[u] = cmul(v[m + u * B], w[(u - 1) * B + m]);
+            }
         }
+        pk_t r[RADIX / 2], i[RADIX / 2];
+        DftSoa<RADIX>::run(x, r, i);
+#pragma unroll
+        for (int u = 0; u < RADIX / 2; ++u) { re[m + u * B] = r[u]; im[m + u * B] = i[u]; }
     }
-    Dft<float, 16>::run_soa(x, re, im);
 }
 #endif
 

@@ -92,7 +92,13 @@ struct FitT {
 // store fills whole 32-byte sectors (a 16-byte half-sector store runs at 0.9 TB/s on
 // B200, a full-sector one at 4.7 TB/s: scratch/ubench_scatter.cu); the row kernel reads
 // its row at a 32-byte stride.
-SB_DEVICE long gbuf_index(int m, int kx, int kpitch) { return ((long)(m >> 1) * kpitch + kx) * 2 + (m & 1); }
+#ifndef SB_GBUF_ROWS
+#define SB_GBUF_ROWS 2
+#endif
+constexpr int kGbufRows = SB_GBUF_ROWS;      // rows interleaved per spectrum column (power of two, even)
+SB_DEVICE long gbuf_index(int m, int kx, int kpitch) {
+    return ((long)(m / kGbufRows) * kpitch + kx) * kGbufRows + (m % kGbufRows);
+}
 
 SB_DEVICE int wrap(int v, int n) {
     int r = v % n;
@@ -559,7 +565,7 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
             const bool direct = k <= N / 2;
             const int kk = direct ? k : N - k;
             C4 w = mk4<R>((R)0, (R)0, (R)0, (R)0);
-            if (active) w = ld4(grow + 2 * kk);
+            if (active) w = ld4(grow + kGbufRows * kk);
             // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
             const C2 x = direct ? mk2<R>(w.x - w.w, w.y + w.z) : mk2<R>(w.x + w.w, w.z - w.y);
             v[q] = mk2<R>(x.y, x.x);

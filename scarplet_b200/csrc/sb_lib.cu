@@ -292,7 +292,8 @@ int plan_axis(const sb_plan* pl, int n, int lo, int hi, AxisPlan* ax) {
         if (cap < 1) continue;
         const int tiles = div_up(n, cap);
         const long cost = (long)tiles * P;
-        if (best_cost < 0 || cost < best_cost) {
+        // equal cost: 4096, the length the pipelined kernels are tuned for, beats 2048
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && P == 4096)) {
             best_cost = cost;
             ax->P = P;
             ax->tiles = tiles;
