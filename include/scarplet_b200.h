@@ -35,7 +35,8 @@ typedef struct sb_angle {
     double sin2_a;  /* np.sin(angle) ** 2   */
 } sb_angle;
 
-enum { SB_KIND_SCARP = 0, SB_KIND_RICKER = 1 };
+enum { SB_KIND_SCARP = 0, SB_KIND_RICKER = 1,
+       SB_KIND_RASTER = 2 /* values supplied by the caller: sb_match_template_raster */ };
 enum { SB_ERRMASK_NONE = 0, SB_ERRMASK_XR_LE0 = 1, SB_ERRMASK_XR_GE0 = 2 };
 
 /* One (scale, age, angle) template: what `Template(scale, age, angle, nx, ny, de)`
@@ -97,6 +98,17 @@ int sb_render_template(sb_plan* plan, const sb_template* tmpl, double* out, int 
 /* core.match_template (core.py:297-377): amp[ny*nx], snr[ny*nx] float64 for one template. */
 int sb_match_template(sb_plan* plan, const sb_angle* angle, const sb_template* tmpl,
                       double* amp, double* snr, int out_is_device);
+
+/* core.match_template for a template the library has no generator for -- the plugin surface
+ * of core.py:345-348: any class with `.template()`.  The caller renders the template on the
+ * host and passes its values on the box of rows sy_lo..sy_hi x columns sx_lo..sx_hi (offsets
+ * from (ny//2, nx//2), row-major float64) that holds every non-zero; outside the box the
+ * template is zero.  amp / snr are the raw planes of core.py:360-367: `get_err_mask` /
+ * `get_window_limits` (core.py:369-375) are the caller's to apply.  tscale: a power of two
+ * near 1 / rms(template) (0 = 1). */
+int sb_match_template_raster(sb_plan* plan, const sb_angle* angle, const double* box_host,
+                             int sy_lo, int sy_hi, int sx_lo, int sx_hi, double tscale,
+                             double* amp, double* snr, int out_is_device);
 
 /* Best-fit state (running result of core.compare over a sweep). */
 int sb_best_reset(sb_plan* plan);

@@ -234,6 +234,47 @@ def match_template(z, dx, dy, kind, scale, age, angle):
     return amp, age, angle, snr
 
 
+def match_template_plugin(z, dx, dy, Template, scale, age, angle, **kwargs):
+    """core.py:339-375 for ANY template class -- the plugin surface of the path: a class
+    callable as ``Template(scale, age, angle, nx, ny, de)`` (core.py:345) with
+    ``template()`` (:346), ``get_window_limits()`` (:373) and optionally ``get_err_mask()``
+    (:369-371).  Same arithmetic as ``match_template`` above."""
+    fft2, ifft2, fftshift = np.fft.fft2, np.fft.ifft2, np.fft.fftshift
+    curv = directional_laplacian(z, dx, dy, angle)           # :340
+    ny, nx = curv.shape
+    template_obj = Template(scale, age, angle, nx, ny, dx, **kwargs)   # :343-345
+    t = template_obj.template()                              # :346
+    M = t != 0                                               # :348
+    fm2 = fft2(M)
+    n = np.sum(M) + EPS                                      # :350
+    fc = fft2(curv)
+    ft = fft2(t)
+    fc2 = fft2(curv ** 2)
+    tsum = np.sum(t ** 2)                                    # :356
+    xcorr = np.real(fftshift(ifft2(ft * fc)))                # :359
+    amp = xcorr / tsum                                       # :360
+    T1 = tsum * (amp ** 2)                                   # :362
+    T3 = fftshift(ifft2(fc2 * fm2))                          # :363
+    with np.errstate(divide='ignore', invalid='ignore'):
+        error = (1 / n) * np.real(T1 - 2 * amp * xcorr + T3) + EPS  # :366
+        snr = np.abs(T1 / error)                             # :367
+    if hasattr(template_obj, 'get_err_mask'):                # :369-371
+        snr[template_obj.get_err_mask()] = 0
+    mask = template_obj.get_window_limits()                  # :373-375
+    amp[mask] = 0
+    snr[mask] = 0
+    return amp, age, angle, snr
+
+
+def calculate_best_fit_parameters_plugin(z, dx, dy, Template, scale, age,
+                                         ang_max=np.pi / 2, ang_min=-np.pi / 2):
+    """core.py:139-195 with a plugin class (serial: the Pool only changes who computes)."""
+    ny, nx = z.shape
+    results = (match_template_plugin(z, dx, dy, Template, scale, age, a)
+               for a in search_angles(ang_min, ang_max))
+    return np.stack(compare(results, ny, nx))                # :186-193
+
+
 def compare(results, ny, nx):
     """Running per-pixel best-SNR select (core.py:198-243).
 

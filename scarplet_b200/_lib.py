@@ -63,6 +63,8 @@ def _declare(lib):
     lib.sb_finalize.argtypes = [P, c_void_p, c_void_p, c_int, c_void_p, c_int]
     lib.sb_best_state.argtypes = [P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.sb_best_pack.argtypes = [P, c_void_p]
+    lib.sb_match_template_raster.argtypes = [P, POINTER(SbAngle), c_void_p, c_int, c_int, c_int, c_int,
+                                             c_double, c_void_p, c_void_p, c_int]
     lib.sb_best_select.argtypes = [P, c_void_p, c_void_p]
     lib.sb_best_unpack.argtypes = [P, c_void_p, c_void_p]
     lib.sb_compare_host.argtypes = [P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -72,7 +74,7 @@ def _declare(lib):
     for name in ("sb_plan_create", "sb_plan_destroy", "sb_plan_set_option",
                  "sb_plan_last_geometry", "sb_plan_profile", "sb_set_dem_host", "sb_set_dem_dev",
                  "sb_set_axes_host", "sb_directional_laplacian", "sb_render_template",
-                 "sb_match_template", "sb_best_reset", "sb_sweep", "sb_finalize",
+                 "sb_match_template", "sb_match_template_raster", "sb_best_reset", "sb_sweep", "sb_finalize",
                  "sb_best_state", "sb_best_pack", "sb_best_select", "sb_best_unpack",
                  "sb_compare_host", "sb_debug_fft", "sb_sync"):
         getattr(lib, name).restype = c_int
@@ -83,7 +85,7 @@ EXPORTED = ("sb_last_error", "sb_build_info", "sb_plan_create", "sb_plan_destroy
             "sb_plan_set_option", "sb_plan_launch_count", "sb_plan_last_geometry", "sb_plan_profile",
             "sb_set_dem_host", "sb_set_dem_dev", "sb_set_axes_host",
             "sb_directional_laplacian", "sb_render_template", "sb_match_template",
-            "sb_best_reset", "sb_sweep", "sb_finalize", "sb_best_state", "sb_best_pack",
+            "sb_match_template_raster", "sb_best_reset", "sb_sweep", "sb_finalize", "sb_best_state", "sb_best_pack",
             "sb_best_select", "sb_best_unpack", "sb_compare_host",
             "sb_debug_fft", "sb_sync")
 

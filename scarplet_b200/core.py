@@ -31,17 +31,66 @@ def _plan_for(data, **plan_kwargs):
     return plan
 
 
+def _plugin_match_template(plan, data, Template, scale, age, angle, **kwargs):
+    """core.py:339-375 for a template class without an on-device generator -- the plugin
+    surface: the class is instantiated and asked for its raster and masks exactly as the
+    reference does; correlation and fit run on the device (``sb_match_template_raster``).
+    One host-rendered raster per call: slow by design, any ``WindowedTemplate`` works."""
+    z, dx, _ = _grid_fields(data)
+    ny, nx = z.shape
+    tobj = Template(scale, age, angle, nx, ny, dx, **kwargs)        # core.py:345
+    amp, snr = plan.match_template_raster(tobj.template(), angle)   # core.py:346-367
+    if hasattr(tobj, 'get_err_mask'):                               # core.py:369-371
+        snr[np.asarray(tobj.get_err_mask(), dtype=bool)] = 0
+    mask = np.asarray(tobj.get_window_limits(), dtype=bool)         # core.py:373-375
+    amp[mask] = 0
+    snr[mask] = 0
+    return amp, snr
+
+
+def _plugin_sweep(data, Template, scale, ages, ang_max, ang_min, order, **kwargs):
+    """The reference's own loops (core.py:100-134, 180-188, 288-291) around
+    ``_plugin_match_template``, folded with ``compare``'s exact semantics."""
+    z, _, _ = _grid_fields(data)
+    ny, nx = z.shape
+    angles = P.search_angles(ang_min, ang_max)
+    with _plan_for(data) as plan:
+        def one(age, angle):
+            amp, snr = _plugin_match_template(plan, data, Template, scale, age, angle, **kwargs)
+            return amp, age, angle, snr
+        if order == "angle_major":                                  # core.py:100-134
+            best = np.zeros((4, ny, nx), dtype=np.float64)
+            for angle in angles:
+                for age in ages:
+                    plan.compare_fold(best, *one(age, angle))
+            return best
+        outer = np.zeros((4, ny, nx), dtype=np.float64)
+        for age in ages:                                            # core.py:288-291
+            best = np.zeros((4, ny, nx), dtype=np.float64)
+            for angle in angles:                                    # core.py:180-188
+                plan.compare_fold(best, *one(age, angle))
+            if len(ages) == 1:
+                return best
+            plan.compare_fold(outer, best[0], best[1], best[2], best[3])
+        return outer
+
+
 def match_template(data, Template, scale, age, angle, **kwargs):
     """Fit one (scale, age, angle) template to the directional curvature
     (core.py:297-377).  Returns ``(amp, age, angle, snr)`` with float64 planes."""
     spec = device_spec(Template)
     with _plan_for(data) as plan:
-        amp, snr = plan.match_template(spec, scale, age, angle)
+        if spec is None:
+            amp, snr = _plugin_match_template(plan, data, Template, scale, age, angle, **kwargs)
+        else:
+            amp, snr = plan.match_template(spec, scale, age, angle)
     return amp, age, angle, snr
 
 
 def _sweep(data, Template, scale, ages, ang_max, ang_min, order, plan=None):
     spec = device_spec(Template)
+    if spec is None:
+        return _plugin_sweep(data, Template, scale, ages, ang_max, ang_min, order)
     angles = P.search_angles(ang_min, ang_max)
     own = plan is None
     if own:

@@ -56,7 +56,7 @@ struct Tmpl {                // one (scale, age, angle) template
     double k0, k1;           // scarp: 2*kt**1.5*sqrt(pi), 4*kt   ricker: pi*f, unused
     double sign;             // -1 for the right-facing upper-break template
     double tscale;           // power of two: t is packed as t * tscale next to M (0/1)
-    int kind;                // 0 scarp family, 1 ricker/channel
+    int kind;                // 0 scarp family, 1 ricker/channel, 2 raster (values from the caller)
     int errmode;             // 0 none, 1 snr=0 where xr<=0, 2 snr=0 where xr>=0
     int sy_lo, sy_hi, sx_lo, sx_hi;   // support box, offsets from (ny//2, nx//2)
     int i_lo, i_hi, j_lo, j_hi;       // un-masked output window (inclusive raster indices)
@@ -320,7 +320,7 @@ template <int N, typename R>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* SB_RESTRICT xvec,
             const double* SB_RESTRICT yvec, typename Vec<R>::v4* SB_RESTRICT trt, double2* SB_RESTRICT part,
-            const typename Vec<R>::v2* SB_RESTRICT tw) {
+            const typename Vec<R>::v2* SB_RESTRICT tw, const double* SB_RESTRICT box) {
     typedef typename Vec<R>::v2 C2;
     typedef typename Vec<R>::v4 C4;
     constexpr int T = N / E;
@@ -343,7 +343,9 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
         const int b = qx < N / 2 ? qx : qx - N;
         C2 val = mk2<R>((R)0, (R)0);
         if (active && b >= p.sx_lo && b <= p.sx_hi) {
-            const double w = template_at(p, sb_ldg(xvec + b0 + b), y);
+            // kind 2: the plugin's own template() values on the support box (core.py:346)
+            const double w = p.kind == 2 ? sb_ldg(box + (long)r * (p.sx_hi - p.sx_lo + 1) + (b - p.sx_lo))
+                                         : template_at(p, sb_ldg(xvec + b0 + b), y);
             if (w != 0.0) {                                   // M = template != 0, core.py:348
                 cnt += 1.0;
                 ssq += w * w;

@@ -82,7 +82,7 @@ struct sb_plan {
     int* d_bidx = nullptr;
     std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
-    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw;
+    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     int conv_persist = std::getenv("SB_CONV_P") ? std::atoi(std::getenv("SB_CONV_P")) : 1;
     int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 0;
@@ -343,6 +343,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                      [](const sb_template& a, const sb_template& b) { return a.angle_id < b.angle_id; });
     int lo_y = 0, hi_y = 0, lo_x = 0, hi_x = 0, syp = 1;
     for (auto& t : tm) {
+        if (t.kind == SB_KIND_RASTER && (n_tmpls != 1 || !pl->tbox.p))
+            return fail("raster templates go through sb_match_template_raster, one at a time");
         if (t.angle_id < 0 || t.angle_id >= n_angles) return fail("template angle_id out of range");
         if (t.sy_hi < t.sy_lo || t.sx_hi < t.sx_lo) return fail("empty template support box");
         if (t.sy_lo < -(pl->ny / 2) || t.sy_hi > pl->ny - 1 - pl->ny / 2 || t.sx_lo < -(pl->nx / 2) ||
@@ -465,7 +467,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                         ProfScope prof(pl, K_TMPL_ROWS);
                         SB_LAUNCH(kern, dim3(div_up(syp, S::GP), cnt), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
-                                  (C4*)pl->trt.p, (double2*)pl->part.p, twx);
+                                  (C4*)pl->trt.p, (double2*)pl->part.p, twx, (const double*)pl->tbox.p);
                         return check_launch(pl, "k_tmpl_rows");
                     }));
                     {
@@ -677,7 +679,7 @@ int sb_plan_destroy(sb_plan* pl) {
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
     for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
     for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                   &pl->tables, &pl->raw})
+                   &pl->tables, &pl->raw, &pl->tbox})
         release(*b);
 #ifndef SB_EMU
     if (pl->own_stream) cudaStreamDestroy(pl->stream);
@@ -817,6 +819,25 @@ int sb_match_template(sb_plan* pl, const sb_angle* angle, const sb_template* tmp
     }
     SB_TRY(sb_rt_sync(pl->stream));
     return 0;
+}
+
+int sb_match_template_raster(sb_plan* pl, const sb_angle* angle, const double* box_host, int sy_lo, int sy_hi,
+                             int sx_lo, int sx_hi, double tscale, double* amp, double* snr, int out_is_device) {
+    if (!pl || !angle || !box_host || !amp || !snr) return fail("sb_match_template_raster: null");
+    if (sy_hi < sy_lo || sx_hi < sx_lo) return fail("sb_match_template_raster: empty box");
+    const size_t cells = (size_t)(sy_hi - sy_lo + 1) * (size_t)(sx_hi - sx_lo + 1);
+    SB_OK(ensure(pl->tbox, cells * sizeof(double)));
+    SB_TRY(sb_rt_h2d(pl->tbox.p, box_host, cells * sizeof(double), pl->stream));
+    sb_template t;
+    std::memset(&t, 0, sizeof(t));
+    t.cos_t = 1.0;
+    t.sign = 1.0;
+    t.tscale = tscale > 0.0 ? tscale : 1.0;
+    t.kind = SB_KIND_RASTER;
+    t.errmode = SB_ERRMASK_NONE;
+    t.sy_lo = sy_lo; t.sy_hi = sy_hi; t.sx_lo = sx_lo; t.sx_hi = sx_hi;
+    t.i_lo = 0; t.i_hi = pl->ny - 1; t.j_lo = 0; t.j_hi = pl->nx - 1;     // masks are the caller's
+    return sb_match_template(pl, angle, &t, amp, snr, out_is_device);
 }
 
 int sb_best_reset(sb_plan* pl) {

@@ -149,6 +149,30 @@ class Plan(object):
                                                    amp.ctypes.data, snr.ctypes.data, 0))
         return amp, snr
 
+    def match_template_raster(self, t, angle):
+        """Raw ``amp, snr`` planes (core.py:359-367, no masks) for a template raster rendered
+        on the host by a plugin class (core.py:345-346); the curvature is taken along
+        ``angle``.  Only the box that holds the raster's non-zeros is uploaded."""
+        t = _as_f64(t)
+        if t.shape != (self.ny, self.nx):
+            raise ValueError("template shape %r does not match the plan %r" % (t.shape, (self.ny, self.nx)))
+        rows = np.flatnonzero(np.any(t != 0, axis=1))
+        cols = np.flatnonzero(np.any(t != 0, axis=0))
+        if len(rows) == 0:
+            raise ValueError("template is zero everywhere")
+        a0, b0 = self.ny // 2, self.nx // 2
+        box = np.ascontiguousarray(t[rows[0]:rows[-1] + 1, cols[0]:cols[-1] + 1])
+        nz = box[box != 0]
+        rms = float(np.sqrt(np.mean(nz * nz)))
+        tscale = float(2.0 ** np.clip(np.round(-np.log2(rms)), -300, 300)) if np.isfinite(rms) and rms > 1e-280 else 1.0
+        a = P.angle_record(angle)
+        amp = np.empty((self.ny, self.nx), dtype=np.float64)
+        snr = np.empty((self.ny, self.nx), dtype=np.float64)
+        check(self.lib, self.lib.sb_match_template_raster(
+            self._h, byref(a), box.ctypes.data, int(rows[0]) - a0, int(rows[-1]) - a0,
+            int(cols[0]) - b0, int(cols[-1]) - b0, tscale, amp.ctypes.data, snr.ctypes.data, 0))
+        return amp, snr
+
     # -- sweeps ------------------------------------------------------------------
     def build_sweep(self, spec, scale, ages, angles, order="age_major", angle_slice=None):
         """Records for the fan-out over ``angles`` x ``ages``.

@@ -136,7 +136,8 @@ def device_spec(Template):
     """Device generator for a template class.  Accepts this package's classes and the
     reference's own built-ins (matched by name when they come from
     ``scarplet.WindowedTemplate``), so ``sl.match(data, scarplet.WindowedTemplate.Scarp)``
-    style call sites keep working."""
+    style call sites keep working.  ``None`` for any other class: it is served through its own
+    ``template()`` / ``get_window_limits()`` / ``get_err_mask()`` methods (core._plugin_*)."""
     spec = getattr(Template, "_sb_spec", None)
     if spec is not None:
         return spec
@@ -144,6 +145,4 @@ def device_spec(Template):
     name = getattr(Template, "__name__", "")
     if mod.startswith("scarplet.") and name in _BUILTIN_BY_NAME:
         return _BUILTIN_BY_NAME[name]._sb_spec
-    raise TypeError(
-        "no on-device generator for template class %r; built-ins: %s"
-        % (Template, ", ".join(sorted(_BUILTIN_BY_NAME))))
+    return None        # a plugin class: core.py renders it on the host (generic path)

@@ -164,3 +164,28 @@ def test_persistent_column_kernel(emu_lib, scale, ages):
     rep = stack_report(outs["1"], np.stack(ref))
     assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.999, rep
     assert rep["snr_rel_p50"] < 1e-5 and rep["frac_snr_over_tol"] <= 2e-2, rep
+
+
+@pytest.mark.parametrize("shape,angle", [((128, 128), 0.3), ((90, 140), -0.8)])
+def test_plugin_template_generic_path(emu_lib, shape, angle):
+    """A template class the library has no generator for (tests/plugin_templates.py) goes
+    through its own template() / get_window_limits() / get_err_mask() (core.py:345-375) and
+    the raster entry point; the oracle's plugin restatement is pinned to the unmodified
+    reference in tests/test_oracle_vs_reference.py."""
+    import scarplet_b200 as sl
+    from scarplet_b200.synth import synthetic_dem
+    from plugin_templates import Ridge
+    z = synthetic_dem(shape[0], seed=11, nx=shape[1], relief=3.0)
+    amp, a, g, snr = sl.match_template(sl.DEMGrid(z, 1.0), Ridge, 9, 1.5, angle)
+    ramp, _, _, rsnr = O.match_template_plugin(z, 1.0, 1.0, Ridge, 9, 1.5, angle)
+    assert a == 1.5 and g == angle
+    assert np.array_equal(snr > 0, rsnr > 0) and np.array_equal(amp != 0, ramp != 0)
+    v = rsnr > 0
+    assert np.abs(amp - ramp)[ramp != 0].max() <= 2e-5 * np.abs(ramp).max()
+    strong = v & (rsnr >= np.median(rsnr[v]))
+    assert (np.abs(snr - rsnr)[strong] / rsnr[strong]).max() < 1e-4
+    # orientation search with compare's exact semantics (core.py:180-193)
+    res = sl.calculate_best_fit_parameters(sl.DEMGrid(z, 1.0), Ridge, 9, 1.5, ang_max=0.06, ang_min=-0.06)
+    ref = O.calculate_best_fit_parameters_plugin(z, 1.0, 1.0, Ridge, 9, 1.5, ang_max=0.06, ang_min=-0.06)
+    rep = stack_report(res, ref, odd_template=False)
+    assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.99, rep

@@ -294,3 +294,29 @@ def test_large_raster_properties(cuda_lib):
     rep = stack_report(sub, rsub)
     assert rep["valid"] > 10000 and rep["index_agreement"] >= INDEX_AGREEMENT, rep
     assert rep["frac_snr_over_tol"] <= 1e-3, rep
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (300, 210)])
+def test_plugin_template_generic_path(cuda_lib, shape):
+    """a user-defined WindowedTemplate (tests/plugin_templates.py), for
+    which the library has no on-device generator, served through its own template() /
+    get_window_limits() / get_err_mask() and sb_match_template_raster."""
+    import scarplet_b200 as sl
+    from scarplet_b200.synth import synthetic_dem
+    from oracle import scarplet_oracle as O
+    from plugin_templates import Ridge
+    z = synthetic_dem(shape[0], seed=shape[1], nx=shape[1])
+    for angle in (0.4, -np.pi / 2):
+        amp, a, g, snr = sl.match_template(sl.DEMGrid(z, 1.0), Ridge, 12, 2.0, angle)
+        ramp, _, _, rsnr = O.match_template_plugin(z, 1.0, 1.0, Ridge, 12, 2.0, angle)
+        assert np.array_equal(snr > 0, rsnr > 0) and np.array_equal(amp != 0, ramp != 0)
+        v = rsnr > 0
+        assert np.abs(amp - ramp)[v].max() <= 2e-5 * np.abs(ramp[v]).max()
+        strong = v & (rsnr >= np.median(rsnr[v]))
+        assert (np.abs(snr - rsnr)[strong] / rsnr[strong]).max() < AMP_SNR_RTOL
+    res = sl.calculate_best_fit_parameters(sl.DEMGrid(z, 1.0), Ridge, 12, 2.0, ang_max=0.2, ang_min=-0.2)
+    ref = O.calculate_best_fit_parameters_plugin(z, 1.0, 1.0, Ridge, 12, 2.0, ang_max=0.2, ang_min=-0.2)
+    rep = stack_report(res, ref, odd_template=False)
+    assert rep["mask_mismatch_unexplained"] == 0, rep
+    assert rep["index_agreement"] >= INDEX_AGREEMENT, rep
+    assert rep["frac_snr_over_tol"] <= 1e-3 and rep["frac_amp_over_tol"] <= 2e-3, rep

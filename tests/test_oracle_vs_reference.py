@@ -58,3 +58,19 @@ def test_search_and_age_sweep_identical(ref):
     oser = O.calculate_best_fit_parameters_serial(z, 1.0, 1.0, O.SCARP, 8, ang_max=0.05, ang_min=-0.05)
     for a, b in zip(ser, oser):
         assert np.array_equal(a, b)
+
+
+def test_plugin_template_identical(ref):
+    """A user-defined template class through the unmodified reference and through the oracle's
+    restatement of the plugin surface (core.py:345-375)."""
+    sl, WT = ref
+    from plugin_templates import Ridge
+    z = _dem(64, 72, 9)
+    grid = ref_import.make_grid(z, 1.0, 1.0)
+    for angle in (-1.1, 0.0, 0.6):
+        amp, _, _, snr = sl.match_template(grid, Ridge, 7, 1.5, angle)
+        oamp, _, _, osnr = O.match_template_plugin(z, 1.0, 1.0, Ridge, 7, 1.5, angle)
+        assert np.array_equal(amp, oamp) and np.array_equal(snr, osnr)
+    res = sl.calculate_best_fit_parameters(grid, Ridge, 7, 1.5, ang_max=0.1, ang_min=-0.1)
+    ores = O.calculate_best_fit_parameters_plugin(z, 1.0, 1.0, Ridge, 7, 1.5, ang_max=0.1, ang_min=-0.1)
+    assert np.array_equal(res, ores)
