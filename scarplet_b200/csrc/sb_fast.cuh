@@ -701,6 +701,7 @@ struct FitPairCtx {
             const float s_lo = fabsf(sb_fdiv_fast(t1.x, err.x));               // core.py:367
             const float s_hi = fabsf(sb_fdiv_fast(t1.y, err.y));
             snr2[j] = make_float2(s_lo, s_hi);
+            // (a NaN SNR -- NaN in the DEM -- never wins here; k_poison_windows marks those pixels)
             cand |= (s_lo >= bs[j] && s_lo > 0.f) ? (1u << j) : 0u;
             cand |= (s_hi >= bs[j + 8] && s_hi > 0.f) ? (1u << (j + 8)) : 0u;
         }
@@ -864,6 +865,25 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
         if ((c.chg >> q) & 1u) best_snr[(long)c.giA * g.nx + g.ox + jo] = bsA[q];
         if ((c.chg >> (q + 16)) & 1u) best_snr[(long)c.giB * g.nx + g.ox + jo] = bsB[q];
     }
+}
+
+// ---------------------------------------------------------------------------
+// k_poison_windows: only launched when the DEM holds a NaN (dem.py:105).  Every FFT output is
+// NaN then, and compare's arithmetic select (core.py:230-240: 0 * best + 0 * NaN) leaves NaN
+// wherever a template is un-masked; the pipelined fit kernels never let a NaN win, so the
+// pixels inside the windows of the batch's templates are marked here.  A NaN best SNR then
+// loses no later comparison.
+// ---------------------------------------------------------------------------
+SB_GLOBAL k_poison_windows(Geom g, int count, const FitT* SB_RESTRICT fit, float* SB_RESTRICT best_snr) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= (long)g.out_ny * g.out_nx) return;
+    const int gi = g.oy + (int)(i / g.out_nx), gj = g.ox + (int)(i % g.out_nx);
+    bool hit = false;
+    for (int p = 0; p < count && !hit; ++p) {
+        const FitT k = fit[p];
+        hit = gi >= k.i_lo && gi <= k.i_hi && gj >= k.j_lo && gj <= k.j_hi;
+    }
+    if (hit) best_snr[(long)gi * g.nx + gj] = NAN;
 }
 
 }  // namespace sb

@@ -44,6 +44,7 @@ struct Geom {
     double norm;             // 1 / (Px * Py)
     double c2_scale;         // power of two: curv**2 is packed as curv**2 * c2_scale next to curv
     int dbg;                 // developer ablation switches (SB_DBG), 0 in production
+    int poison;              // the DEM holds a NaN: every FFT domain gets one (the reference's fft2 spans the raster)
 };
 
 struct Angle {               // one search orientation (curvature direction)
@@ -232,7 +233,10 @@ SB_DEVICE void hermitian_split(const typename Vec<R>::v2 (&v)[E], int t, typenam
 }
 
 // ---------------------------------------------------------------------------
-// k_curv_rows<Px>: grid (ceil(need_rows / GP), n_angles)
+// k_curv_rows<Px>: grid (n_angles, ceil(need_rows / GP)) -- the angle runs fastest, so the CTAs
+// that read the same rows of the second-difference planes (24 B/px, float64) are co-resident
+// and all but the first of them find the rows in L2 (row-fastest order re-read the planes from
+// DRAM for every angle: 32 B/px per angle measured, 8.4 after).
 // ---------------------------------------------------------------------------
 template <int N, typename R>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
@@ -245,9 +249,9 @@ k_curv_rows(Geom g, const double* SB_RESTRICT diffs, const Angle* SB_RESTRICT an
     constexpr int GP = (T > 256 ? T : 256) / T;
     C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int need_rows = g.need_y_hi - g.need_y_lo + 1;
-    const int r = sb_bx() * GP + grp;
+    const int r = sb_by() * GP + grp;
     const bool active = r < need_rows;
-    const int a_loc = sb_by();
+    const int a_loc = sb_bx();
     const Angle ang = angles[angle_base + a_loc];
     C2 v[E];
     const int gi = wrap(g.oy + g.need_y_lo + (active ? r : 0), g.ny);
@@ -262,6 +266,7 @@ k_curv_rows(Geom g, const double* SB_RESTRICT diffs, const Angle* SB_RESTRICT an
             const double c = combine_curvature(sb_ldg(diffs + o), sb_ldg(diffs + n + o), sb_ldg(diffs + 2 * n + o), ang);
             val = mk2<R>((R)c, (R)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
         }
+        if (g.poison && r == 0 && qx == 0) val = mk2<R>((R)NAN, (R)NAN);
         v[q] = val;
     }
     sbfft::forward<N, R>(v, t, sm, tw);
@@ -613,7 +618,10 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
             } else {
                 // first maximum wins (core.py:230-240); equal positive SNRs resolve to the
                 // lower flat index so the result does not depend on batch order
-                if (snr_f > bs[q] || (snr_f == bs[q] && snr_f > 0.f && p.idx < bi[q])) {
+                // a NaN SNR (NaN in the DEM) sticks: 0 * best + 0 * NaN (core.py:230-240)
+                if (snr_f != snr_f) {
+                    bs[q] = snr_f;
+                } else if (snr_f > bs[q] || (snr_f == bs[q] && snr_f > 0.f && p.idx < bi[q])) {
                     bs[q] = snr_f;
                     ba[q] = amp_f;
                     bi[q] = p.idx;
@@ -691,10 +699,14 @@ SB_GLOBAL k_finalize(long n, const float* SB_RESTRICT snr, const float* SB_RESTR
     const float s = snr[i];
     const int k = idx[i];
     const bool hit = s > 0.f && k != 0x7fffffff;
-    out4[i] = hit ? (double)amp[i] : 0.0;
+    // NaN in the DEM (dem.py:105): compare's select leaves NaN in amp and snr and 0 in age and
+    // angle wherever some template was un-masked
+    const bool nan = s != s;
+    const double qnan = (double)s;
+    out4[i] = nan ? qnan : hit ? (double)amp[i] : 0.0;
     out4[n + i] = hit ? age_of[k] : 0.0;
     out4[2 * n + i] = hit ? angle_of[k] : 0.0;
-    out4[3 * n + i] = hit ? (double)s : 0.0;
+    out4[3 * n + i] = nan ? qnan : hit ? (double)s : 0.0;
 }
 
 // sum over the raster of dxx**2 + dyy**2 (per-block partials, fixed order): gives the

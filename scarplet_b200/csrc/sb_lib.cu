@@ -88,6 +88,7 @@ struct sb_plan {
     int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 0;
     long launches = 0;
     double c2_scale = 1.0;
+    bool dem_nonfinite = false;    // the DEM holds a NaN / Inf: every FFT domain is poisoned like the reference's
     int profile = 0;
     std::vector<sb_event_t> ev_pool;
     struct EvPair { int kind; sb_event_t a, b; };
@@ -265,6 +266,9 @@ int update_curv_scale(sb_plan* pl) {
     pl->c2_scale = 1.0;
     if (std::isfinite(sigma) && sigma > 1e-150 && sigma < 1e150)
         pl->c2_scale = std::exp2(std::round(-std::log2(sigma)));
+    // a NaN anywhere in the DEM reaches every output pixel through the reference's full-raster
+    // fft2 (dem.py:105, core.py:353-363); tiles that do not hold the cell have to be told
+    pl->dem_nonfinite = !std::isfinite(sum);
     return 0;
 }
 
@@ -431,6 +435,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
             g.norm = 1.0 / ((double)Px * (double)Py);
             g.c2_scale = pl->c2_scale;
             g.dbg = std::getenv("SB_DBG") ? std::atoi(std::getenv("SB_DBG")) : 0;
+            g.poison = pl->dem_nonfinite ? 1 : 0;
             const int need_rows = g.need_y_hi - g.need_y_lo + 1;
 
             for (int a0 = 0; a0 < n_angles; a0 += Ba) {
@@ -443,7 +448,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                     auto kern = sb::k_curv_rows<N, R>;
                     SB_ALLOW_SMEM(kern, S::smem);
                     ProfScope prof(pl, K_CURV_ROWS);
-                    SB_LAUNCH(kern, dim3(div_up(need_rows, S::GP), a1 - a0), dim3(S::threads),
+                    SB_LAUNCH(kern, dim3(a1 - a0, div_up(need_rows, S::GP)), dim3(S::threads),
                               S::smem, pl->stream, g, (const double*)pl->d_diffs, d_an, a0, (C4*)pl->cr.p, twx);
                     return check_launch(pl, "k_curv_rows");
                 }));
@@ -561,6 +566,11 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                 }
                                 return check_launch(pl, "k_fit_rows_f");
                             }));
+                            if (g.poison) {
+                                SB_LAUNCH(sb::k_poison_windows, dim3(div_up((long)g.out_ny * g.out_nx, 256)), dim3(256), 0,
+                                          pl->stream, g, cnt, (const sb::FitT*)pl->fit.p, pl->d_bsnr);
+                                SB_OK(check_launch(pl, "k_poison_windows"));
+                            }
                         }
                     }
                     if (!fast) {

@@ -189,3 +189,24 @@ def test_plugin_template_generic_path(emu_lib, shape, angle):
     ref = O.calculate_best_fit_parameters_plugin(z, 1.0, 1.0, Ridge, 9, 1.5, ang_max=0.06, ang_min=-0.06)
     rep = stack_report(res, ref, odd_template=False)
     assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.99, rep
+
+
+def test_nan_in_dem_search(emu_lib):
+    """one NaN in the DEM spreads through fft2; compare's arithmetic select
+    (core.py:230-240) then leaves NaN in amp / snr wherever some orientation is un-masked, 0
+    in age / angle, and 0 where every orientation is edge-masked.  The input is not modified
+    (the reference zero-fills it in place, dem.py:85-86)."""
+    import scarplet_b200 as sl
+    from scarplet_b200.WindowedTemplate import Scarp
+    from scarplet_b200.synth import synthetic_dem
+    z = synthetic_dem(96, seed=3, nx=128, relief=3.0)
+    z[40, 77] = np.nan
+    keep = z.copy()
+    res = sl.calculate_best_fit_parameters(sl.DEMGrid(z, 1.0), Scarp, 8, 2.0, ang_max=0.3, ang_min=-0.3)
+    ref = O.calculate_best_fit_parameters(z, 1.0, 1.0, O.SCARP, 8, 2.0, ang_max=0.3, ang_min=-0.3)
+    assert np.array_equal(z, keep, equal_nan=True)
+    assert np.isnan(ref[3]).any() and (ref[3] == 0).any()
+    for plane in (0, 3):
+        assert np.array_equal(np.isnan(res[plane]), np.isnan(ref[plane]))
+        assert np.array_equal(res[plane] == 0, ref[plane] == 0)
+    assert np.array_equal(res[1], ref[1]) and np.array_equal(res[2], ref[2])

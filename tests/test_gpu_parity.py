@@ -320,3 +320,24 @@ def test_plugin_template_generic_path(cuda_lib, shape):
     assert rep["mask_mismatch_unexplained"] == 0, rep
     assert rep["index_agreement"] >= INDEX_AGREEMENT, rep
     assert rep["frac_snr_over_tol"] <= 1e-3 and rep["frac_amp_over_tol"] <= 2e-3, rep
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (200, 333)])
+def test_nan_in_dem_search(cuda_lib, shape):
+    """a NaN in the DEM => NaN amp / snr wherever some orientation is un-masked,
+    zeros in age / angle and in the always-masked border; the caller's DEM is not modified."""
+    import scarplet_b200 as sl
+    from scarplet_b200.WindowedTemplate import Scarp
+    from scarplet_b200.synth import synthetic_dem
+    from oracle import scarplet_oracle as O
+    z = synthetic_dem(shape[0], seed=7, nx=shape[1])
+    z[shape[0] // 3, shape[1] // 2] = np.nan
+    keep = z.copy()
+    res = sl.calculate_best_fit_parameters(sl.DEMGrid(z, 1.0), Scarp, 16, 5.0)
+    ref = O.calculate_best_fit_parameters(z, 1.0, 1.0, O.SCARP, 16, 5.0, processes=8)
+    assert np.array_equal(z, keep, equal_nan=True)
+    assert np.isnan(ref[3]).any() and (ref[3] == 0).any()
+    for plane in (0, 3):
+        assert np.array_equal(np.isnan(res[plane]), np.isnan(ref[plane]))
+        assert np.array_equal(res[plane] == 0, ref[plane] == 0)
+    assert np.array_equal(res[1], ref[1]) and np.array_equal(res[2], ref[2])
