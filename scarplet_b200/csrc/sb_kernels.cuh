@@ -39,7 +39,8 @@ struct Geom {
     int need_y_lo, need_y_hi;  // signed offsets of the domain rows that carry curvature
     int need_x_lo, need_x_hi;
     int kpitch;              // pitch (elements) of half-spectrum rows
-    int syp;                 // pitch (rows) of the per-template support block
+    int syp;                 // pitch (rows, even) of the per-template support block
+    int rpitch;              // pitch (rows, even) of the transposed curvature row spectra
     double dx, dx2, dy2;     // cell size, dx**2, dy**2 as the host computes them
     double norm;             // 1 / (Px * Py)
     double c2_scale;         // power of two: curv**2 is packed as curv**2 * c2_scale next to curv
@@ -232,8 +233,40 @@ SB_DEVICE void hermitian_split(const typename Vec<R>::v2 (&v)[E], int t, typenam
     sb_sync();
 }
 
+// The same split into registers: h[q] for k = t + q*T (q < E/2), h[E/2] for k = N/2 (thread 0).
+template <int N, typename R>
+SB_DEVICE void hermitian_split_regs(const typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm,
+                                    typename Vec<R>::v4 (&h)[E / 2 + 1]) {
+    typedef typename Vec<R>::v2 C2;
+    constexpr int T = N / E;
+#pragma unroll
+    for (int q = 0; q < E; ++q) sm[sbfft::pad_index(t + q * T)] = v[q];
+    sb_sync();
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+        const int k = t + q * T;
+        const C2 zp = sm[sbfft::pad_index((N - k) & (N - 1))];
+        const C2 a = v[q];
+        h[q] = mk4<R>((R)0.5 * (a.x + zp.x), (R)0.5 * (a.y - zp.y), (R)0.5 * (a.y + zp.y), -(R)0.5 * (a.x - zp.x));
+    }
+    h[E / 2] = mk4<R>(v[E / 2].x, (R)0, v[E / 2].y, (R)0);      // Nyquist, index N/2 = (E/2)*T
+    sb_sync();
+}
+
+// Row pair (2p, 2p + 1) of a transposed plane [kx][pitch rows]: both rows' values of one kx
+// leave in one store, so the column kernels read their inputs fully coalesced and the row
+// kernels write whole sectors (a 16-byte strided store runs at a fifth of the rate).
+template <int N, typename R>
+SB_DEVICE void store_row_pair(const typename Vec<R>::v4 (&h0)[E / 2 + 1], const typename Vec<R>::v4 (&h1)[E / 2 + 1],
+                              int t, typename Vec<R>::v4* out, long pitch) {
+    constexpr int T = N / E;
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) sb_st_pair(out + (long)(t + q * T) * pitch, h0[q], h1[q]);
+    if (t == 0) sb_st_pair(out + (long)(N / 2) * pitch, h0[E / 2], h1[E / 2]);
+}
+
 // ---------------------------------------------------------------------------
-// k_curv_rows<Px>: grid (n_angles, ceil(need_rows / GP)) -- the angle runs fastest, so the CTAs
+// k_curv_rows<Px>: grid (n_angles, ceil(need_rows / 2 / GP)), a row pair per thread group -- the angle runs fastest, so the CTAs
 // that read the same rows of the second-difference planes (24 B/px, float64) are co-resident
 // and all but the first of them find the rows in L2 (row-fastest order re-read the planes from
 // DRAM for every angle: 32 B/px per angle measured, 8.4 after).
@@ -249,29 +282,38 @@ k_curv_rows(Geom g, const double* SB_RESTRICT diffs, const Angle* SB_RESTRICT an
     constexpr int GP = (T > 256 ? T : 256) / T;
     C2* sm = (C2*)sb_shared() + grp * sbfft::padded_len(N);
     const int need_rows = g.need_y_hi - g.need_y_lo + 1;
-    const int r = sb_by() * GP + grp;
-    const bool active = r < need_rows;
+    const int rp = sb_by() * GP + grp;                 // row pair (2 rp, 2 rp + 1)
     const int a_loc = sb_bx();
     const Angle ang = angles[angle_base + a_loc];
-    C2 v[E];
-    const int gi = wrap(g.oy + g.need_y_lo + (active ? r : 0), g.ny);
+    const int KX = N / 2 + 1;
+    C4 h0[E / 2 + 1], h1[E / 2 + 1];
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int qx = t + q * T;
-        const int sx = qx < g.split_x ? qx : qx - N;
-        C2 val = mk2<R>((R)0, (R)0);
-        if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
-            const int gj = wrap(g.ox + sx, g.nx);
-            const long o = (long)gi * g.nx + gj, n = (long)g.ny * g.nx;
-            const double c = combine_curvature(sb_ldg(diffs + o), sb_ldg(diffs + n + o), sb_ldg(diffs + 2 * n + o), ang);
-            val = mk2<R>((R)c, (R)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
+    for (int f = 0; f < 2; ++f) {
+        const int r = 2 * rp + f;
+        const bool active = r < need_rows;
+        C2 v[E];
+        const int gi = wrap(g.oy + g.need_y_lo + (active ? r : 0), g.ny);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int qx = t + q * T;
+            const int sx = qx < g.split_x ? qx : qx - N;
+            C2 val = mk2<R>((R)0, (R)0);
+            if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
+                const int gj = wrap(g.ox + sx, g.nx);
+                const long o = (long)gi * g.nx + gj, n = (long)g.ny * g.nx;
+                const double c = combine_curvature(sb_ldg(diffs + o), sb_ldg(diffs + n + o), sb_ldg(diffs + 2 * n + o), ang);
+                val = mk2<R>((R)c, (R)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
+            }
+            if (g.poison && r == 0 && qx == 0) val = mk2<R>((R)NAN, (R)NAN);
+            v[q] = val;
         }
-        if (g.poison && r == 0 && qx == 0) val = mk2<R>((R)NAN, (R)NAN);
-        v[q] = val;
+        sbfft::forward<N, R>(v, t, sm, tw);
+        if (f == 0) hermitian_split_regs<N, R>(v, t, sm, h0);
+        else hermitian_split_regs<N, R>(v, t, sm, h1);
     }
-    sbfft::forward<N, R>(v, t, sm, tw);
-    C4* out = cr + ((long)a_loc * need_rows + (active ? r : 0)) * g.kpitch;
-    hermitian_split<N, R>(v, t, sm, out, 1, active);
+    // cr layout: [angle][kx][rpitch rows] C4 (F_row[curv], F_row[curv**2 * c2_scale])
+    if (2 * rp < need_rows)
+        store_row_pair<N, R>(h0, h1, t, cr + (long)a_loc * KX * g.rpitch + 2 * rp, g.rpitch);
 }
 
 // ---------------------------------------------------------------------------
@@ -293,33 +335,57 @@ k_curv_cols(Geom g, const typename Vec<R>::v4* SB_RESTRICT cr, typename Vec<R>::
     const int kx = sb_bx() * GP + grp;
     const bool active = kx < KX;
     const int a_loc = sb_by();
-    const C4* src = cr + (long)a_loc * need_rows * g.kpitch + (active ? kx : 0);
-#pragma unroll 1
-    for (int f = 0; f < 2; ++f) {
-        C2 v[E];
+    const C4* src = cr + ((long)a_loc * KX + (active ? kx : 0)) * g.rpitch;     // [angle][kx][row]: coalesced
+    if constexpr (sizeof(R) == 4) {
+        // both fields from one read of the plane
+        C4 w[E];
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int qy = t + q * T;
             const int sy = qy < g.split_y ? qy : qy - N;
-            C2 val = mk2<R>((R)0, (R)0);
-            if (active && sy >= g.need_y_lo && sy <= g.need_y_hi) {
-                const C4 w = ld4(src + (long)(sy - g.need_y_lo) * g.kpitch);
-                val = f == 0 ? mk2<R>(w.x, w.y) : mk2<R>(w.z, w.w);
-            }
-            v[q] = val;
+            w[q] = mk4<R>((R)0, (R)0, (R)0, (R)0);
+            if (active && sy >= g.need_y_lo && sy <= g.need_y_hi) w[q] = sb_ld_stream(src + (sy - g.need_y_lo));
         }
-        sbfft::forward<N, R>(v, t, sm, tw);
-        if (active) {
-            C2* dst = fct + (((long)a_loc * 2 + f) * KX + kx) * N;
 #pragma unroll
-            for (int q = 0; q < E; ++q) dst[t + q * T] = v[q];
+        for (int f = 0; f < 2; ++f) {
+            C2 v[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) v[q] = f == 0 ? mk2<R>(w[q].x, w[q].y) : mk2<R>(w[q].z, w[q].w);
+            sbfft::forward<N, R>(v, t, sm, tw);
+            if (active) {
+                C2* dst = fct + (((long)a_loc * 2 + f) * KX + kx) * N;
+#pragma unroll
+                for (int q = 0; q < E; ++q) dst[t + q * T] = v[q];
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int f = 0; f < 2; ++f) {
+            C2 v[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const int qy = t + q * T;
+                const int sy = qy < g.split_y ? qy : qy - N;
+                C2 val = mk2<R>((R)0, (R)0);
+                if (active && sy >= g.need_y_lo && sy <= g.need_y_hi) {
+                    const C4 w = ld4(src + (sy - g.need_y_lo));
+                    val = f == 0 ? mk2<R>(w.x, w.y) : mk2<R>(w.z, w.w);
+                }
+                v[q] = val;
+            }
+            sbfft::forward<N, R>(v, t, sm, tw);
+            if (active) {
+                C2* dst = fct + (((long)a_loc * 2 + f) * KX + kx) * N;
+#pragma unroll
+                for (int q = 0; q < E; ++q) dst[t + q * T] = v[q];
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// k_tmpl_rows<Px>: grid (ceil(syp / GP), n_templates)
-// trt layout: [template][kx][syp] C4 (F_row[t], F_row[M]);  part: [template][syp] double2
+// k_tmpl_rows<Px>: grid (ceil(syp / 2 / GP), n_templates), a row pair per thread group
+// trt layout: [template][kx][syp] C4 (F_row[t], F_row[M]), syp even;  part: [template][syp] double2
 // ---------------------------------------------------------------------------
 template <int N, typename R>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
@@ -335,51 +401,58 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
     const int p_loc = sb_by();
     const Tmpl p = tmpls[tmpl_base + p_loc];
     const int rows = p.sy_hi - p.sy_lo + 1;
-    const int r = sb_bx() * GP + grp;
-    const bool active = r < rows;
+    const int rp = sb_bx() * GP + grp;                 // row pair (2 rp, 2 rp + 1) of the support box
     const int KX = N / 2 + 1;
     const int a0 = g.ny / 2, b0 = g.nx / 2;
-    C2 v[E];
-    double cnt = 0.0, ssq = 0.0;
-    const double y = active ? sb_ldg(yvec + a0 + p.sy_lo + r) : 0.0;
+    C4 h0[E / 2 + 1], h1[E / 2 + 1];
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int qx = t + q * T;
-        const int b = qx < N / 2 ? qx : qx - N;
-        C2 val = mk2<R>((R)0, (R)0);
-        if (active && b >= p.sx_lo && b <= p.sx_hi) {
-            // kind 2: the plugin's own template() values on the support box (core.py:346)
-            const double w = p.kind == 2 ? sb_ldg(box + (long)r * (p.sx_hi - p.sx_lo + 1) + (b - p.sx_lo))
-                                         : template_at(p, sb_ldg(xvec + b0 + b), y);
-            if (w != 0.0) {                                   // M = template != 0, core.py:348
-                cnt += 1.0;
-                ssq += w * w;
-                val = mk2<R>((R)(w * p.tscale), (R)1);
+    for (int f = 0; f < 2; ++f) {
+        const int r = 2 * rp + f;
+        const bool active = r < rows;
+        C2 v[E];
+        double cnt = 0.0, ssq = 0.0;
+        const double y = active ? sb_ldg(yvec + a0 + p.sy_lo + r) : 0.0;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int qx = t + q * T;
+            const int b = qx < N / 2 ? qx : qx - N;
+            C2 val = mk2<R>((R)0, (R)0);
+            if (active && b >= p.sx_lo && b <= p.sx_hi) {
+                // kind 2: the plugin's own template() values on the support box (core.py:346)
+                const double w = p.kind == 2 ? sb_ldg(box + (long)r * (p.sx_hi - p.sx_lo + 1) + (b - p.sx_lo))
+                                             : template_at(p, sb_ldg(xvec + b0 + b), y);
+                if (w != 0.0) {                                   // M = template != 0, core.py:348
+                    cnt += 1.0;
+                    ssq += w * w;
+                    val = mk2<R>((R)(w * p.tscale), (R)1);
+                }
             }
+            v[q] = val;
         }
-        v[q] = val;
+        // deterministic per-row sums of M and t^2 (two-level, fixed order)
+        {
+            double2* sd = (double2*)sm;
+            sd[t] = make_double2(cnt, ssq);
+            sb_sync();
+            if ((t & 15) == 0) {
+                double a = 0.0, b = 0.0;
+                for (int i = 0; i < 16 && t + i < T; ++i) { a += sd[t + i].x; b += sd[t + i].y; }
+                sd[t] = make_double2(a, b);
+            }
+            sb_sync();
+            if (t == 0) {
+                double a = 0.0, b = 0.0;
+                for (int i = 0; i < T; i += 16) { a += sd[i].x; b += sd[i].y; }
+                if (active) part[(long)p_loc * g.syp + r] = make_double2(a, b);
+            }
+            sb_sync();
+        }
+        sbfft::forward<N, R>(v, t, sm, tw);
+        if (f == 0) hermitian_split_regs<N, R>(v, t, sm, h0);
+        else hermitian_split_regs<N, R>(v, t, sm, h1);
     }
-    // deterministic per-row sums of M and t^2 (two-level, fixed order)
-    {
-        double2* sd = (double2*)sm;
-        sd[t] = make_double2(cnt, ssq);
-        sb_sync();
-        if ((t & 15) == 0) {
-            double a = 0.0, b = 0.0;
-            for (int i = 0; i < 16 && t + i < T; ++i) { a += sd[t + i].x; b += sd[t + i].y; }
-            sd[t] = make_double2(a, b);
-        }
-        sb_sync();
-        if (t == 0) {
-            double a = 0.0, b = 0.0;
-            for (int i = 0; i < T; i += 16) { a += sd[i].x; b += sd[i].y; }
-            if (active) part[(long)p_loc * g.syp + r] = make_double2(a, b);
-        }
-        sb_sync();
-    }
-    sbfft::forward<N, R>(v, t, sm, tw);
-    C4* out = trt + (long)p_loc * KX * g.syp + (active ? r : 0);
-    hermitian_split<N, R>(v, t, sm, out, g.syp, active);
+    if (2 * rp < rows)
+        store_row_pair<N, R>(h0, h1, t, trt + (long)p_loc * KX * g.syp + 2 * rp, g.syp);
 }
 
 // one thread per template: fixed-order sum of the per-row partials

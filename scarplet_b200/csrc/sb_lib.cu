@@ -360,6 +360,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
         hi_x = std::max(hi_x, t.sx_hi);
         syp = std::max(syp, t.sy_hi - t.sy_lo + 1);
     }
+    syp += syp & 1;      // the row kernels store row pairs
     AxisPlan ay, ax;
     SB_OK(plan_axis(pl, pl->ny, lo_y, hi_y, &ay));
     SB_OK(plan_axis(pl, pl->nx, lo_x, hi_x, &ax));
@@ -373,7 +374,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
 
     // batch sizes from the workspace budget
     const int need_rows_max = ay.periodic ? Py : std::min(Py, ay.tile_out + (hi_y - lo_y) + 2);
-    const size_t per_angle = (size_t)need_rows_max * kpitch * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
+    const size_t per_angle = (size_t)(need_rows_max + 1) * KX * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
     const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)Py * kpitch * sizeof(C4) +
                             (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
     size_t budget = (size_t)pl->workspace_mb << 20;
@@ -401,7 +402,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     if (max_per_angle > 1 && Bt >= max_per_angle) Bt = (Bt / max_per_angle) * max_per_angle;
     else if (Bt > 1) Bt &= ~1;       // k_fit_rows_f walks the batch two templates at a time
 
-    SB_OK(ensure(pl->cr, (size_t)Ba * need_rows_max * kpitch * sizeof(C4)));
+    const int rpitch_max = need_rows_max + (need_rows_max & 1);
+    SB_OK(ensure(pl->cr, (size_t)Ba * KX * rpitch_max * sizeof(C4)));
     SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(C2)));
     SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(C4)));
     SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
@@ -437,6 +439,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
             g.dbg = std::getenv("SB_DBG") ? std::atoi(std::getenv("SB_DBG")) : 0;
             g.poison = pl->dem_nonfinite ? 1 : 0;
             const int need_rows = g.need_y_hi - g.need_y_lo + 1;
+            g.rpitch = need_rows + (need_rows & 1);
 
             for (int a0 = 0; a0 < n_angles; a0 += Ba) {
                 const int a1 = std::min(n_angles, a0 + Ba);
@@ -448,7 +451,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                     auto kern = sb::k_curv_rows<N, R>;
                     SB_ALLOW_SMEM(kern, S::smem);
                     ProfScope prof(pl, K_CURV_ROWS);
-                    SB_LAUNCH(kern, dim3(a1 - a0, div_up(need_rows, S::GP)), dim3(S::threads),
+                    SB_LAUNCH(kern, dim3(a1 - a0, div_up(div_up(need_rows, 2), S::GP)), dim3(S::threads),
                               S::smem, pl->stream, g, (const double*)pl->d_diffs, d_an, a0, (C4*)pl->cr.p, twx);
                     return check_launch(pl, "k_curv_rows");
                 }));
@@ -470,7 +473,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                         auto kern = sb::k_tmpl_rows<N, R>;
                         SB_ALLOW_SMEM(kern, S::smem);
                         ProfScope prof(pl, K_TMPL_ROWS);
-                        SB_LAUNCH(kern, dim3(div_up(syp, S::GP), cnt), dim3(S::threads), S::smem,
+                        SB_LAUNCH(kern, dim3(div_up(syp / 2, S::GP), cnt), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
                                   (C4*)pl->trt.p, (double2*)pl->part.p, twx, (const double*)pl->tbox.p);
                         return check_launch(pl, "k_tmpl_rows");

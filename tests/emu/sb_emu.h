@@ -197,6 +197,8 @@ SB_DEVICE float2 sb_ld_stream(const float2* p) { return *p; }
 SB_DEVICE float4 sb_ld_stream(const float4* p) { return *p; }
 SB_DEVICE float4 sb_ld_shared_soon(const float4* p) { return *p; }
 SB_DEVICE void sb_st_stream(float4* p, float4 v) { *p = v; }
+SB_DEVICE void sb_st_pair(float4* p, float4 a, float4 b) { p[0] = a; p[1] = b; }
+SB_DEVICE void sb_st_pair(double4* p, double4 a, double4 b) { p[0] = a; p[1] = b; }
 SB_DEVICE void sb_ld_sector(const float4* p, float4& a, float4& b) { a = p[0]; b = p[1]; }
 SB_DEVICE float sb_fdiv_fast(float a, float b) { return a / b; }
 
