@@ -84,7 +84,10 @@ struct sb_plan {
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
     Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
-    int conv_persist = std::getenv("SB_CONV_P") ? std::atoi(std::getenv("SB_CONV_P")) : 1;
+    // persistent column kernel: 1 always, 0 never, -1 (default) when a search angle carries at least
+    // four templates -- with fewer, half of its thread groups idle and the per-angle staging of
+    // the spectrum columns is not amortised (C2: 94 ms persistent, 69 ms per-template)
+    int conv_persist = std::getenv("SB_CONV_P") ? std::atoi(std::getenv("SB_CONV_P")) : -1;
     int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 0;
     long launches = 0;
     double c2_scale = 1.0;
@@ -497,7 +500,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                 const bool sparse = hi_y <= S::T - 1 && lo_y >= -S::T;
                                 ProfScope prof(pl, K_CONV_COLS);
                                 if constexpr (N >= 1024 && N <= 4096) {
-                                    if (pl->conv_persist && cnt <= sb::kConvPMaxBatch) {
+                                    const bool persist = pl->conv_persist > 0 || (pl->conv_persist < 0 && max_per_angle >= 4);
+                                    if (persist && cnt <= sb::kConvPMaxBatch) {
                                         constexpr size_t smem_p =
                                             (size_t)(sb::kConvPThreads / S::T) * 2 * sbfft::padded_len(N) * sizeof(float2) +
                                             (size_t)2 * N * sizeof(float2) + sb::kConvPMaxBatch * 4 * sizeof(int) +

@@ -120,7 +120,9 @@ def main():
         res, info = timed_search(z, Channel._sb_spec, 10, [0.1], angles, repeats=3)
         info["finite"] = bool(np.isfinite(res).all())
         # Ricker support along xr: exp underflow at u^2 > 745 => |xr| < 87 px; no edge mask
-        info["parity_crop"] = crop_parity(z, res, O.RICKER, 10, [0.1], 1500, 700, 110, odd=False)
+        # the crop must have the raster's parity (odd): the template's pixel-centre offsets are
+        # half-integer on an even axis (WindowedTemplate.py:50-53)
+        info["parity_crop"] = crop_parity(z, res, O.RICKER, 10, [0.1], 1500, 701, 110, odd=False)
         results["C2 Channel scale=10 age=0.1, 3601^2 (dx=1)"] = info
         print("c2 done", file=sys.stderr)
 
