@@ -868,6 +868,118 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
 }
 
 // ---------------------------------------------------------------------------
+// k_curv_rows_f<Px>: pipelined k_curv_rows (complex64): the two rows of a pair are the two
+// transforms a thread group carries (one barrier per exchange); grid and layouts as k_curv_rows.
+// ---------------------------------------------------------------------------
+template <int N>
+struct CurvCtx {
+    static constexpr int K = sbfft::num_stages(N);
+    static constexpr int T = N / E;
+    int t;
+    float2 *smA, *smB;
+    const float2* tw;
+    const float4* diffs;               // [pixel][dxx, dxy, dyy, -] float32
+    float ca2, sc2, sa2;               // cos**2, 2 sin cos, sin**2 of the search angle
+    int oy, ox, ny, nx, need_y_lo, need_x_lo, need_x_hi, split_x, poison, dbg;
+    float c2_scale;
+    int rp;                            // row pair: rows 2 rp (stream a) and 2 rp + 1 (stream b)
+    int need_rows;
+
+    SB_DEVICE void bar() const { sb_sync(); }
+    template <int P> SB_DEVICE void twid(float2 (&w)[TW]) { sbfft::load_tw<N, P, float>(w, t, tw); }
+
+    template <int F> SB_DEVICE void fill(float2 (&v)[E]) const {
+        const int r = 2 * rp + F;
+        const bool active = r < need_rows;
+        const int gi = wrap(oy + need_y_lo + (active ? r : 0), ny);
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int qx = t + q * T;
+            const int sx = qx < split_x ? qx : qx - N;
+            float2 val = make_float2(0.f, 0.f);
+            if (active && sx >= need_x_lo && sx <= need_x_hi) {
+                const int gj = wrap(ox + sx, nx);
+                const long o = (long)gi * nx + gj;
+                // dem.py:103-104 on the float32 second differences: the transform rounds the
+                // curvature to float32 anyway, and one 16-byte load replaces three 8-byte ones
+                const float4 d = SB_DBG_ON(dbg, 256) ? make_float4((float)o * 1e-9f, 1.f, 2.f, 0.f) : sb_ldg(diffs + o);
+                const float c = (d.x * ca2 - d.y * sc2) + d.z * sa2;
+                val = make_float2(c, c * c * c2_scale);                    // curv, curv**2 (core.py:355)
+            }
+            if (poison && r == 0 && qx == 0) val = make_float2(NAN, NAN);
+            v[q] = val;
+        }
+    }
+    template <int P, int F> SB_DEVICE void phase(float2 (&v)[E], const float2 (&w)[TW]) {
+        sbfft::stage_math<N, P, float>(v, w);       // both rows are filled before the pipeline starts
+    }
+    template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
+        sbfft::stage_store<N, P, float>(v, t, F == 0 ? smA : smB);
+    }
+    template <int F> SB_DEVICE void load(float2 (&v)[E]) { sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB); }
+};
+
+// Hermitian split (sb_kernels.cuh) of the spectrum parked in natural order in `sm`
+template <int N>
+SB_DEVICE void split_from_shared(const float2* sm, int t, float4 (&h)[E / 2 + 1]) {
+    constexpr int T = N / E;
+#pragma unroll
+    for (int q = 0; q < E / 2; ++q) {
+        const int k = t + q * T;
+        const float2 a = sm[sbfft::pad_index(k)];
+        const float2 zp = sm[sbfft::pad_index((N - k) & (N - 1))];
+        h[q] = make_float4(0.5f * (a.x + zp.x), 0.5f * (a.y - zp.y), 0.5f * (a.y + zp.y), -0.5f * (a.x - zp.x));
+    }
+    const float2 ny = sm[sbfft::pad_index(N / 2)];
+    h[E / 2] = make_float4(ny.x, 0.f, ny.y, 0.f);
+}
+
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_curv_rows_f(Geom g, const float4* SB_RESTRICT diffs, const Angle* SB_RESTRICT angles, int angle_base,
+              float4* SB_RESTRICT cr, const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    constexpr int PL = sbfft::padded_len(N);
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    const int KX = N / 2 + 1;
+    const int a_loc = sb_bx();
+    CurvCtx<N> c;
+    c.t = t;
+    c.smA = (float2*)sb_shared() + (long)grp * 2 * PL;
+    c.smB = c.smA + PL;
+    c.tw = tw;
+    c.diffs = diffs;
+    c.oy = g.oy; c.ox = g.ox; c.ny = g.ny; c.nx = g.nx;
+    c.need_y_lo = g.need_y_lo; c.need_x_lo = g.need_x_lo; c.need_x_hi = g.need_x_hi;
+    c.split_x = g.split_x; c.poison = g.poison; c.c2_scale = (float)g.c2_scale; c.dbg = g.dbg;
+    {
+        const Angle ang = angles[angle_base + a_loc];
+        c.ca2 = (float)ang.ca2;
+        c.sc2 = (float)(2.0 * ang.sa * ang.ca);
+        c.sa2 = (float)ang.sa2;
+    }
+    c.rp = sb_by() * GP + grp;
+    c.need_rows = g.need_y_hi - g.need_y_lo + 1;
+    float2 va[E], vb[E];
+    c.template fill<0>(va);                     // all 32 loads of the pair in flight together
+    c.template fill<1>(vb);
+    leapfrog<CurvCtx<N>::K>(c, va, vb);
+    sb_sync();                                  // every thread is done with the exchange buffers
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        c.smA[sbfft::pad_index(t + q * T)] = va[q];
+        c.smB[sbfft::pad_index(t + q * T)] = vb[q];
+    }
+    sb_sync();
+    float4 h0[E / 2 + 1], h1[E / 2 + 1];
+    split_from_shared<N>(c.smA, t, h0);
+    split_from_shared<N>(c.smB, t, h1);
+    if (2 * c.rp < c.need_rows)
+        store_row_pair<N, float>(h0, h1, t, cr + (long)a_loc * KX * g.rpitch + 2 * c.rp, g.rpitch);
+}
+
+// ---------------------------------------------------------------------------
 // k_poison_windows: only launched when the DEM holds a NaN (dem.py:105).  Every FFT output is
 // NaN then, and compare's arithmetic select (core.py:230-240: 0 * best + 0 * NaN) leaves NaN
 // wherever a template is un-masked; the pipelined fit kernels never let a NaN win, so the

@@ -162,8 +162,10 @@ SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int i
 }
 
 // the DEM's second differences, computed once per DEM: planes [dxx][dxy][dyy] of ny*nx
+// out32: the same three planes rounded to float32, interleaved [pixel][dxx, dxy, dyy, 0], for the
+// complex64 pipeline (its curvature is rounded to float32 before the transform anyway)
 SB_GLOBAL k_second_differences(int ny, int nx, const double* SB_RESTRICT dem, double dx, double dx2,
-                               double dy2, double* SB_RESTRICT out) {
+                               double dy2, double* SB_RESTRICT out, float4* SB_RESTRICT out32) {
     const long n = (long)ny * nx;
     const long i = (long)sb_bx() * 256 + sb_tid();
     if (i >= n) return;
@@ -171,6 +173,7 @@ SB_GLOBAL k_second_differences(int ny, int nx, const double* SB_RESTRICT dem, do
     out[i] = d.dxx;
     out[n + i] = d.dxy;
     out[2 * n + i] = d.dyy;
+    out32[i] = make_float4((float)d.dxx, (float)d.dxy, (float)d.dyy, 0.f);
 }
 
 // ---------------------------------------------------------------------------

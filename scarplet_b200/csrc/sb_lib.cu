@@ -75,6 +75,7 @@ struct sb_plan {
     double* d_dem = nullptr;
     bool own_dem = false;
     double* d_diffs = nullptr;      // dxx, dxy, dyy planes of the current DEM (dem.py:88-99)
+    float4* d_diffs32 = nullptr;    // the same, float32, interleaved per pixel (complex64 pipeline)
     double* d_x = nullptr;
     double* d_y = nullptr;
     float* d_bsnr = nullptr;
@@ -251,8 +252,9 @@ int update_curv_scale(sb_plan* pl) {
     {   // the angle-independent second differences, once per DEM
         const long n = (long)pl->ny * pl->nx;
         if (!pl->d_diffs) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs, (size_t)n * 3 * sizeof(double)));
+        if (!pl->d_diffs32) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs32, (size_t)n * sizeof(float4)));
         SB_LAUNCH(sb::k_second_differences, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx,
-                  (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, pl->d_diffs);
+                  (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, pl->d_diffs, pl->d_diffs32);
         SB_OK(check_launch(pl, "k_second_differences"));
     }
     const int blocks = std::max(1, std::min(1024, div_up((long)pl->ny * pl->nx, 256)));
@@ -448,6 +450,19 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                 const int a1 = std::min(n_angles, a0 + Ba);
                 const int p0 = first[a0], p1 = first[a1];
                 if (p1 == p0) continue;
+                if (std::is_same<R, float>::value && pl->fast) {
+                    SB_OK(dispatch_n(Px, [&](auto nn) {
+                        constexpr int N = decltype(nn)::value;
+                        using S = Shape<N, float>;
+                        auto kern = sb::k_curv_rows_f<N>;
+                        SB_ALLOW_SMEM(kern, S::smem_conv_f);
+                        ProfScope prof(pl, K_CURV_ROWS);
+                        SB_LAUNCH(kern, dim3(a1 - a0, div_up(div_up(need_rows, 2), S::GP)), dim3(S::threads),
+                                  S::smem_conv_f, pl->stream, g, (const float4*)pl->d_diffs32, d_an, a0,
+                                  (float4*)pl->cr.p, (const float2*)twx);
+                        return check_launch(pl, "k_curv_rows_f");
+                    }));
+                } else
                 SB_OK(dispatch_n(Px, [&](auto nn) {
                     constexpr int N = decltype(nn)::value;
                     using S = Shape<N, R>;
@@ -688,6 +703,7 @@ int sb_plan_destroy(sb_plan* pl) {
     sb_rt_sync(pl->stream);
     if (pl->own_dem && pl->d_dem) sb_rt_free(pl->d_dem);
     if (pl->d_diffs) sb_rt_free(pl->d_diffs);
+    if (pl->d_diffs32) sb_rt_free(pl->d_diffs32);
     if (pl->d_x) sb_rt_free(pl->d_x);
     if (pl->d_y) sb_rt_free(pl->d_y);
     if (pl->d_bsnr) sb_rt_free(pl->d_bsnr);
