@@ -102,6 +102,7 @@ struct ConvCtx {
     int kx, dly, out_ny, kpitch;
     int dbg;
     int bar_id;                       // PERSIST: named barrier of this thread group
+    const float2* va_fin;             // SB_CONV_KEEP_A: field a's registers (the array handed to leapfrog)
 
     SB_DEVICE void bar() const {
 #ifdef SB_ABL_NOBAR
@@ -135,18 +136,25 @@ struct ConvCtx {
             }
             sbfft::stage_math<N, 0, float>(v, w);
         }
+#define SB_CONV_KEEP_A 1    // field a's result waits in registers for field b (parking it in shared memory: +2 %)
+#ifndef SB_CONV_KEEP_A
         if constexpr (P == K - 1 && F == 0) {
             // field a is done; park it in its own (now idle) exchange buffer, every thread in
             // the slots only it will read back, so that its registers are free for field b
 #pragma unroll
             for (int q = 0; q < E; ++q) smA[t + q * T] = v[q];
         }
+#endif
         if constexpr (P == K - 1 && F == 1) {
             if (dst) {
 #pragma unroll
                 for (int q = 0; q < E; ++q) {
                     const int io = (t + q * T + dly) & (N - 1);
+#ifdef SB_CONV_KEEP_A
+                    const float2 a = va_fin[q];      // field a's result, still in the caller's registers
+#else
                     const float2 a = smA[t + q * T];
+#endif
                     if (SB_DBG_ON(dbg, 1) && v[q].x != 1.2345e-30f) continue;
                     if (SB_DBG_ON(dbg, 128)) {      // timing only: same bytes, fully coalesced
                         sb_st_stream(dst + ((long)kx * N + t + q * T), make_float4(a.y, a.x, v[q].y, v[q].x));
@@ -222,6 +230,7 @@ k_conv_cols_f(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_ba
             vb[q] = make_float2(w.z, w.w);
         }
     }
+    c.va_fin = va;
     leapfrog<ConvCtx<N, SPARSE>::K>(c, va, vb);     // the last phase of field b writes gbuf
 }
 
@@ -337,8 +346,11 @@ k_conv_cols_p(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int
                     }
                 }
             }
+            c.va_fin = va;
             leapfrog<Ctx::K>(c, va, vb);                    // the last phase of field b writes gbuf
+#ifndef SB_CONV_KEEP_A
             c.bar();                                        // parked field a has been read back
+#endif
         }
         s0 = s1;
     }
