@@ -910,7 +910,7 @@ struct CurvCtx {
             const int sx = qx < split_x ? qx : qx - N;
             float2 val = make_float2(0.f, 0.f);
             if (active && sx >= need_x_lo && sx <= need_x_hi) {
-                const int gj = wrap(ox + sx, nx);
+                const int gj = wrap_near(ox + sx, nx);
                 const long o = (long)gi * nx + gj;
                 // dem.py:103-104 on the float32 second differences: the transform rounds the
                 // curvature to float32 anyway, and one 16-byte load replaces three 8-byte ones

@@ -102,6 +102,16 @@ SB_DEVICE long gbuf_index(int m, int kx, int kpitch) {
     return ((long)(m / kGbufRows) * kpitch + kx) * kGbufRows + (m % kGbufRows);
 }
 
+// periodic index for v in [-2n, 3n): the halo of a tile never reaches further (the support box
+// lies inside the raster); four predicated adds instead of an integer division per pixel
+SB_DEVICE int wrap_near(int v, int n) {
+    v += v < 0 ? n : 0;
+    v += v < 0 ? n : 0;
+    v -= v >= n ? n : 0;
+    v -= v >= n ? n : 0;
+    return v;
+}
+
 SB_DEVICE int wrap(int v, int n) {
     int r = v % n;
     return r < 0 ? r + n : r;
