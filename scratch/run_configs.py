@@ -28,7 +28,7 @@ from scarplet_b200.synth import synthetic_dem  # noqa: E402
 from scarplet_b200.templates import Channel, Scarp  # noqa: E402
 
 KEEP = ("valid", "index_agreement", "mask_mismatch_unexplained", "tie_reset_pixels", "snr_rel_p50",
-        "snr_rel_max", "amp_rel_max", "frac_snr_over_tol", "frac_amp_over_tol")
+        "snr_rel_max", "amp_rel_max", "frac_snr_over_tol", "frac_amp_over_tol", "disagree_snr_gap_max")
 
 
 def big_dem(n, seed):
