@@ -7,7 +7,8 @@ Drop-in for the reference's ``import scarplet as sl`` on that path::
     res = sl.match(data, Scarp, scale=100, age=10, ang_min=-np.pi / 2, ang_max=np.pi / 2)
 """
 from .core import (calculate_best_fit_parameters,  # noqa: F401
-                   calculate_best_fit_parameters_serial, compare, match, match_template)
+                   calculate_best_fit_parameters_serial, compare, match, match_scales,
+                   match_template)
 from .dem import DEMGrid  # noqa: F401
 from .engine import configure  # noqa: F401
 from . import WindowedTemplate  # noqa: F401

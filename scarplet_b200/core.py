@@ -136,6 +136,33 @@ def match(data, Template, **kwargs):
     return out[0], out[1], out[2], out[3]
 
 
+def match_scales(data, Template, scales, **kwargs):
+    """One ``match`` result per template scale -- the multi-scale product the reference
+    publishes as one 4-band raster per scale (CHANGELOG.md:20-24), which its users obtain by
+    calling ``match`` in a loop (core.py:266-294 per scale).  The DEM is uploaded and its
+    second differences are built once; every scale is its own search with its own best state.
+    Returns ``{scale: result}`` with ``result`` exactly what ``match(..., scale=scale)`` returns."""
+    spec = device_spec(Template)
+    out = {}
+    if spec is None:
+        for scale in scales:
+            out[scale] = match(data, Template, scale=scale, **kwargs)
+        return out
+    ang_max = kwargs.get('ang_max', np.pi / 2)
+    ang_min = kwargs.get('ang_min', -np.pi / 2)
+    with _plan_for(data) as plan:
+        for scale in scales:
+            if 'age' in kwargs:
+                out[scale] = _sweep(data, Template, scale, [kwargs['age']], ang_max, ang_min,
+                                    "age_major", plan=plan)
+            else:
+                ages = kwargs.get('ages', None)
+                ages = P.default_ages() if ages is None else np.asarray(ages, dtype=np.float64)
+                res = _sweep(data, Template, scale, ages, ang_max, ang_min, "age_major", plan=plan)
+                out[scale] = (res[0], res[1], res[2], res[3])
+    return out
+
+
 def compare(results, ny, nx):
     """Per-pixel best-SNR select over an iterable of ``(amp, age, angle, snr)``
     (core.py:198-243), with the reference's exact semantics (strict compares, an

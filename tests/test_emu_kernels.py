@@ -210,3 +210,20 @@ def test_nan_in_dem_search(emu_lib):
         assert np.array_equal(np.isnan(res[plane]), np.isnan(ref[plane]))
         assert np.array_equal(res[plane] == 0, ref[plane] == 0)
     assert np.array_equal(res[1], ref[1]) and np.array_equal(res[2], ref[2])
+
+
+def test_match_scales_equals_per_scale_match(emu_lib):
+    """The multi-scale entry (one result per scale, DEM set-up shared) returns exactly what
+    match() returns for each scale on its own."""
+    import scarplet_b200 as sl
+    from scarplet_b200.WindowedTemplate import Scarp
+    from scarplet_b200.synth import synthetic_dem
+    z = synthetic_dem(96, seed=8, nx=128, relief=3.0)
+    grid = sl.DEMGrid(z, 1.0)
+    multi = sl.match_scales(grid, Scarp, [6, 10], age=3.0, ang_min=-0.2, ang_max=0.2)
+    for scale in (6, 10):
+        single = sl.match(grid, Scarp, scale=scale, age=3.0, ang_min=-0.2, ang_max=0.2)
+        assert np.array_equal(multi[scale], single)
+    sweep = sl.match_scales(grid, Scarp, [8], ages=[2.0, 9.0], ang_min=-0.1, ang_max=0.1)
+    ref = sl.match(grid, Scarp, scale=8, ages=[2.0, 9.0], ang_min=-0.1, ang_max=0.1)
+    assert isinstance(sweep[8], tuple) and all(np.array_equal(a, b) for a, b in zip(sweep[8], ref))

@@ -341,3 +341,22 @@ def test_nan_in_dem_search(cuda_lib, shape):
         assert np.array_equal(np.isnan(res[plane]), np.isnan(ref[plane]))
         assert np.array_equal(res[plane] == 0, ref[plane] == 0)
     assert np.array_equal(res[1], ref[1]) and np.array_equal(res[2], ref[2])
+
+
+def test_match_scales(cuda_lib):
+    """C4's shape: one (4, ny, nx) stack per template scale from one call; each equals the
+    single-scale search and the oracle."""
+    import scarplet_b200 as sl
+    from scarplet_b200.WindowedTemplate import Scarp
+    from scarplet_b200.synth import synthetic_dem
+    from oracle import scarplet_oracle as O
+    z = synthetic_dem(300, seed=12, nx=260)
+    grid = sl.DEMGrid(z, 1.0)
+    multi = sl.match_scales(grid, Scarp, [10, 20, 40], age=10.0)
+    assert sorted(multi) == [10, 20, 40]
+    for scale in (10, 40):
+        assert np.array_equal(multi[scale], sl.match(grid, Scarp, scale=scale, age=10.0))
+        ref = O.calculate_best_fit_parameters(z, 1.0, 1.0, O.SCARP, scale, 10.0, processes=8)
+        rep = stack_report(multi[scale], ref)
+        assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= INDEX_AGREEMENT, rep
+        assert rep["frac_snr_over_tol"] <= 1e-3, rep
