@@ -513,11 +513,13 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     const int grp = sb_tid() / T, t = sb_tid() % T;
     float2* sm = (float2*)sb_shared();
     FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
-    int* s_list = (int*)(s_fit + kFitMaxBatch);          // [kFitMaxBatch] active templates, then their count
-    int* s_flag = s_list + kFitMaxBatch + 1;             // [kFitMaxBatch]
+    // [kFitMaxBatch] active templates, [kFitMaxBatch] flags (16-byte aligned: the compiler reads
+    // them with vector loads), then the count -- s_list[2 * kFitMaxBatch]
+    int* s_list = (int*)(s_fit + kFitMaxBatch);
+    int* s_flag = s_list + kFitMaxBatch;
     // the twiddle table next to the data: 30 table reads per thread and template would
     // otherwise compete with the streamed planes for L1 and mostly come back from L2
-    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 1);
+    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 2);
     sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), THREADS);
     const int io = sb_bx() * GP + grp;
     const bool active = io < g.out_ny;
@@ -536,10 +538,10 @@ k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
         int pos = 0;
         for (int i = 0; i < sb_tid(); ++i) pos += s_flag[i];
         if (s_flag[sb_tid()]) s_list[pos] = sb_tid();
-        if (sb_tid() == count - 1) s_list[kFitMaxBatch] = pos + s_flag[sb_tid()];
+        if (sb_tid() == count - 1) s_list[2 * kFitMaxBatch] = pos + s_flag[sb_tid()];
     }
     sb_sync();
-    const int n_act = s_list[kFitMaxBatch];
+    const int n_act = s_list[2 * kFitMaxBatch];
 
     float bs[E], ba[E];
     unsigned bw[E / 4];
@@ -793,9 +795,11 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     const int grp = sb_tid() / T, t = sb_tid() % T;
     float2* sm = (float2*)sb_shared();
     FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
-    int* s_list = (int*)(s_fit + kFitMaxBatch);          // [kFitMaxBatch] active templates, then their count
-    int* s_flag = s_list + kFitMaxBatch + 1;             // [kFitMaxBatch]
-    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 1);
+    // [kFitMaxBatch] active templates, [kFitMaxBatch] flags (16-byte aligned: the compiler reads
+    // them with vector loads), then the count -- s_list[2 * kFitMaxBatch]
+    int* s_list = (int*)(s_fit + kFitMaxBatch);
+    int* s_flag = s_list + kFitMaxBatch;
+    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 2);
     sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), THREADS);
     const int pairs = g.Py / 2;
     const int pr = min(sb_bx() * GP + grp, pairs - 1);    // row pair of the FFT domain
@@ -820,10 +824,10 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
         int pos = 0;
         for (int i = 0; i < sb_tid(); ++i) pos += s_flag[i];
         if (s_flag[sb_tid()]) s_list[pos] = sb_tid();
-        if (sb_tid() == count - 1) s_list[kFitMaxBatch] = pos + s_flag[sb_tid()];
+        if (sb_tid() == count - 1) s_list[2 * kFitMaxBatch] = pos + s_flag[sb_tid()];
     }
     sb_sync();
-    const int n_act = s_list[kFitMaxBatch];
+    const int n_act = s_list[2 * kFitMaxBatch];
 
     float bsA[E], bsB[E];
     float2 va[E], vb[E];

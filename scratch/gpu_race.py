@@ -1,17 +1,21 @@
-import sys, os; sys.path.insert(0,'.')
+"""Small age sweep through every pipelined kernel (persistent column kernel included), for
+compute-sanitizer --tool racecheck / memcheck."""
+import os, sys
 import numpy as np
-import scarplet_b200 as sl
-from scarplet_b200.synth import synthetic_dem
-from scarplet_b200.WindowedTemplate import Channel
-from scarplet_b200.engine import Plan
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 from scarplet_b200 import params as P
-z = synthetic_dem(257, seed=255, nx=255)
-nang = int(sys.argv[1]) if len(sys.argv) > 1 else 181
-angles = P.search_angles(-np.pi/2, np.pi/2)[:nang]
-outs = []
-with Plan(257, 255, 1.0, 1.0) as plan:
-    plan.set_dem(z)
-    a, t, age_of, angle_of = plan.build_sweep(Channel._sb_spec, 8, [0.15], angles)
-    for it in range(3):
-        plan.reset(); plan.sweep(a, t); outs.append(plan.finalize(age_of, angle_of))
-print('deterministic:', np.array_equal(outs[0], outs[1]), np.array_equal(outs[1], outs[2]), 'diff px', (outs[0][3] != outs[1][3]).sum())
+from scarplet_b200.engine import Plan
+from scarplet_b200.synth import synthetic_dem
+from scarplet_b200.templates import Scarp
+
+for shape in ((1024, 256), (300, 260)):
+    z = synthetic_dem(shape[0], seed=3, nx=shape[1])
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)[::16]
+    with Plan(shape[0], shape[1], 1.0, 1.0) as plan:
+        plan.set_dem(z)
+        a, t, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, 12, [2.0, 5.0, 10.0, 20.0, 40.0], angles)
+        plan.reset()
+        plan.sweep(a, t)
+        out = plan.finalize(age_of, angle_of)
+        print(shape, plan.last_geometry(), float(np.nanmax(out[3])))
