@@ -508,6 +508,20 @@ struct Stages {
     }
 };
 
+// Forward FFT whose only non-zero inputs are v[0] and v[15] (a signal supported on fewer than
+// T samples either side of the origin): the first radix-16 stage is 8 constant products.
+template <int N, typename R>
+SB_DEVICE void forward_sparse2(typename Vec<R>::v2 (&v)[E], int t, typename Vec<R>::v2* sm,
+                               const typename Vec<R>::v2* SB_RESTRICT tw) {
+    static_assert(stage_radix(N, 0) == 16 && num_stages(N) >= 2, "forward_sparse2: N >= 256");
+    stage0_sparse2<R>(v);
+    stage_store<N, 0, R>(v, t, sm);
+    sb_sync();
+    stage_load<N, R>(v, t, sm);
+    sb_sync();
+    Stages<N, R, 1>::run(v, t, sm, tw);
+}
+
 // Forward FFT of length N over the group's registers.  `sm` is the group's
 // private exchange buffer of padded_len(N) elements.  All threads of the CTA must
 // call this together (it contains CTA-wide barriers).

@@ -400,7 +400,11 @@ k_curv_cols(Geom g, const typename Vec<R>::v4* SB_RESTRICT cr, typename Vec<R>::
 // k_tmpl_rows<Px>: grid (ceil(syp / 2 / GP), n_templates), a row pair per thread group
 // trt layout: [template][kx][syp] C4 (F_row[t], F_row[M]), syp even;  part: [template][syp] double2
 // ---------------------------------------------------------------------------
-template <int N, typename R>
+// XSPARSE: every template of the batch is narrower than T columns either side of the centre,
+// so a thread's only non-zero samples are its first and its last: two template evaluations
+// per row instead of sixteen guarded ones (the unrolled float64 exp made this the largest
+// kernel of the library, 70 KB of code), and a sparse first FFT stage.
+template <int N, typename R, bool XSPARSE>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
 k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* SB_RESTRICT xvec,
             const double* SB_RESTRICT yvec, typename Vec<R>::v4* SB_RESTRICT trt, double2* SB_RESTRICT part,
@@ -430,6 +434,7 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
             const int qx = t + q * T;
             const int b = qx < N / 2 ? qx : qx - N;
             C2 val = mk2<R>((R)0, (R)0);
+            if (XSPARSE && q != 0 && q != E - 1) { v[q] = val; continue; }
             if (active && b >= p.sx_lo && b <= p.sx_hi) {
                 // kind 2: the plugin's own template() values on the support box (core.py:346)
                 const double w = p.kind == 2 ? sb_ldg(box + (long)r * (p.sx_hi - p.sx_lo + 1) + (b - p.sx_lo))
@@ -460,7 +465,8 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
             }
             sb_sync();
         }
-        sbfft::forward<N, R>(v, t, sm, tw);
+        if constexpr (XSPARSE) sbfft::forward_sparse2<N, R>(v, t, sm, tw);
+        else sbfft::forward<N, R>(v, t, sm, tw);
         if (f == 0) hermitian_split_regs<N, R>(v, t, sm, h0);
         else hermitian_split_regs<N, R>(v, t, sm, h1);
     }

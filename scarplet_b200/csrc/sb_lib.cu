@@ -488,9 +488,20 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, R>;
-                        auto kern = sb::k_tmpl_rows<N, R>;
-                        SB_ALLOW_SMEM(kern, S::smem);
                         ProfScope prof(pl, K_TMPL_ROWS);
+                        // narrow templates: two samples per thread (needs a radix-16 first stage)
+                        if constexpr (N >= 256) {
+                            if (hi_x <= S::T - 1 && lo_x >= -S::T) {
+                                auto kern = sb::k_tmpl_rows<N, R, true>;
+                                SB_ALLOW_SMEM(kern, S::smem);
+                                SB_LAUNCH(kern, dim3(div_up(syp / 2, S::GP), cnt), dim3(S::threads), S::smem,
+                                          pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
+                                          (C4*)pl->trt.p, (double2*)pl->part.p, twx, (const double*)pl->tbox.p);
+                                return check_launch(pl, "k_tmpl_rows");
+                            }
+                        }
+                        auto kern = sb::k_tmpl_rows<N, R, false>;
+                        SB_ALLOW_SMEM(kern, S::smem);
                         SB_LAUNCH(kern, dim3(div_up(syp / 2, S::GP), cnt), dim3(S::threads), S::smem,
                                   pl->stream, g, d_tm, pb, (const double*)pl->d_x, (const double*)pl->d_y,
                                   (C4*)pl->trt.p, (double2*)pl->part.p, twx, (const double*)pl->tbox.p);
