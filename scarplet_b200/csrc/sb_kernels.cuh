@@ -474,19 +474,29 @@ k_tmpl_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, const double* 
         store_row_pair<N, R>(h0, h1, t, trt + (long)p_loc * KX * g.syp + 2 * rp, g.syp);
 }
 
-// one thread per template: fixed-order sum of the per-row partials
+// fixed-order sum of the per-row partials of each template
 SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
                       const double2* SB_RESTRICT part, TSum* SB_RESTRICT sums, FitT* SB_RESTRICT fit) {
-    const int p_loc = sb_bx() * 32 + sb_tid();
+    // one 32-thread block per template: lane l adds rows l, l + 32, ..., lane 0 adds the 32
+    // partial sums in lane order (fixed order: the result does not depend on the launch)
+    const int p_loc = sb_bx();
     if (p_loc >= count) return;
     const Tmpl p = tmpls[tmpl_base + p_loc];
     const int rows = p.sy_hi - p.sy_lo + 1;
-    double n = 0.0, ts = 0.0;
-    for (int r = 0; r < rows; ++r) {
-        const double2 v = part[(long)p_loc * g.syp + r];
-        n += v.x;
-        ts += v.y;
+    double2* sd = (double2*)sb_shared();
+    {
+        double a = 0.0, b = 0.0;
+        for (int r = sb_tid(); r < rows; r += 32) {
+            const double2 v = part[(long)p_loc * g.syp + r];
+            a += v.x;
+            b += v.y;
+        }
+        sd[sb_tid()] = make_double2(a, b);
     }
+    sb_sync();
+    if (sb_tid() != 0) return;
+    double n = 0.0, ts = 0.0;
+    for (int l = 0; l < 32; ++l) { n += sd[l].x; ts += sd[l].y; }
     TSum s;
     s.n_eps = n + kEps;
     s.ts = ts;

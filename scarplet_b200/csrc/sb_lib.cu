@@ -509,7 +509,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                     }));
                     {
                         ProfScope prof(pl, K_TMPL_SUMS);
-                        SB_LAUNCH(sb::k_tmpl_sums, dim3(div_up(cnt, 32)), dim3(32), 0, pl->stream, g, d_tm, pb, cnt,
+                        SB_LAUNCH(sb::k_tmpl_sums, dim3(cnt), dim3(32), 32 * sizeof(double2), pl->stream, g, d_tm, pb, cnt,
                                   (const double2*)pl->part.p, (sb::TSum*)pl->sums.p, (sb::FitT*)pl->fit.p);
                         SB_OK(check_launch(pl, "k_tmpl_sums"));
                     }
