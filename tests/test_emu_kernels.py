@@ -227,3 +227,31 @@ def test_match_scales_equals_per_scale_match(emu_lib):
     sweep = sl.match_scales(grid, Scarp, [8], ages=[2.0, 9.0], ang_min=-0.1, ang_max=0.1)
     ref = sl.match(grid, Scarp, scale=8, ages=[2.0, 9.0], ang_min=-0.1, ang_max=0.1)
     assert isinstance(sweep[8], tuple) and all(np.array_equal(a, b) for a, b in zip(sweep[8], ref))
+
+
+def test_results_of_one_plan_never_alias(emu_lib):
+    """A long-lived plan hands out pooled (page-locked on a GPU box) result arrays from its
+    second result on; an array is only reused once the caller has dropped it and its views."""
+    from scarplet_b200 import params as P
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.synth import synthetic_dem
+    from scarplet_b200.templates import Scarp
+    z = synthetic_dem(64, seed=2, nx=64, relief=3.0)
+    angles = P.search_angles(-0.05, 0.05)
+    with Plan(64, 64, 1.0, 1.0) as plan:
+        plan.set_dem(z)
+        a, t, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, 6, [2.0], angles)
+        held = []
+        for _ in range(5):
+            plan.reset()
+            plan.sweep(a, t)
+            held.append(plan.finalize(age_of, angle_of))
+        assert len({id(h) for h in held}) == 5
+        for h in held[1:]:
+            assert not np.shares_memory(h, held[0]) and np.array_equal(h, held[0])
+        view = held[4][3]
+        del held
+        plan.reset()
+        plan.sweep(a, t)
+        again = plan.finalize(age_of, angle_of)
+        assert not np.shares_memory(again, view)

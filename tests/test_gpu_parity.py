@@ -360,3 +360,34 @@ def test_match_scales(cuda_lib):
         rep = stack_report(multi[scale], ref)
         assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= INDEX_AGREEMENT, rep
         assert rep["frac_snr_over_tol"] <= 1e-3, rep
+
+
+def test_results_of_one_plan_never_alias(cuda_lib):
+    """Pooled page-locked result arrays (engine.Plan._result_array): reused only after the
+    caller has dropped the array and every view of it."""
+    from scarplet_b200 import params as P
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.synth import synthetic_dem
+    from scarplet_b200.templates import Scarp
+    z = synthetic_dem(256, seed=2)
+    angles = P.search_angles(-0.1, 0.1)
+    with Plan(256, 256, 1.0, 1.0) as plan:
+        plan.set_dem(z)
+        a, t, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, 12, [5.0], angles)
+        held = []
+        for _ in range(6):                      # more than the pool holds
+            plan.reset()
+            plan.sweep(a, t)
+            held.append(plan.finalize(age_of, angle_of))
+        for i, h in enumerate(held[1:]):
+            assert all(not np.shares_memory(h, o) for o in held[:i + 1])
+            assert np.array_equal(h, held[0])
+        view = held[3][3]
+        keep = view.copy()
+        del held, h
+        for _ in range(4):
+            plan.reset()
+            plan.sweep(a, t)
+            again = plan.finalize(age_of, angle_of)
+            assert not np.shares_memory(again, view)
+        assert np.array_equal(view, keep)
