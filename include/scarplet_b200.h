@@ -55,6 +55,9 @@ typedef struct sb_template {
     int32_t i_lo, i_hi, j_lo, j_hi;     /* rows/cols NOT masked by get_window_limits (inclusive) */
     int32_t angle_id;     /* index into the sb_angle array                                  */
     int32_t idx;          /* flat result index: tie priority and key into age_of/angle_of   */
+    int32_t state;        /* best state the template folds into (0 .. option "states" - 1): one per
+                             template scale in a multi-scale search (CHANGELOG.md:20-24)    */
+    int32_t reserved;     /* 0 */
 } sb_template;
 
 /* flags for sb_plan_create */
@@ -71,16 +74,39 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
                    int device, void* stream, unsigned flags);
 int sb_plan_destroy(sb_plan* plan);
 
-/* tuning knobs: key in {"workspace_mb", "max_fft", "force_pad", "profile",
- * "precision" (32 = complex64 pipeline, default; 64 = complex128 pipeline)}; returns 0 if known */
+/* knobs: key in {"workspace_mb", "max_fft", "force_pad", "mixed_tiles", "profile", "conv_persist",
+ * "precision" (32 = complex64 pipeline, default; 64 = complex128 pipeline),
+ * "states" (number of independent best states, default 1; resets them)}; returns 0 if known */
 int sb_plan_set_option(sb_plan* plan, const char* key, long value);
+
+/* Spatial sharding of one raster over several GPUs (BASELINE config 5; the reference's
+ * analogue is file-level tiling, dem.py:249-278).  The plan keeps the geometry of the WHOLE raster
+ * (template centring, edge masks and the circular wrap-around of core.py:359 are evaluated in
+ * full-raster coordinates) but computes only raster rows row_lo .. row_hi - 1 and holds only the
+ * DEM rows row_lo - halo .. row_hi + halo - 1 (periodic in ny).  Call before sb_set_dem_*; the DEM
+ * handed to sb_set_dem_* is then that slab (sb_plan_dem_rows: first raster row, row count).
+ * halo >= template support along y + 2.  The best state covers the plan's rows only. */
+int sb_plan_set_slab(sb_plan* plan, int row_lo, int row_hi, int halo);
+int sb_plan_dem_rows(const sb_plan* plan, int* row0, int* drows);
+/* curvature statistics of the plan's own rows (sum of dxx^2 + dyy^2, pixel count): a non-finite
+ * sum marks a NaN in the DEM.  Slabs of one raster add theirs up and hand the totals back, so that
+ * every rank packs with the same scale and knows about a NaN held by another (dem.py:105). */
+int sb_plan_curv_stats(const sb_plan* plan, double* sumsq, double* count);
+int sb_plan_set_curv_stats(sb_plan* plan, double sumsq, double count);
+/* the cudaStream_t the plan's work is ordered on */
+void* sb_plan_stream(const sb_plan* plan);
+/* device memory held by the plan (bytes) */
+long sb_plan_device_bytes(const sb_plan* plan);
+/* sum over the FFT tiles of the last sweep of Py * Px (tiling overhead = this / (rows * nx)) */
+double sb_plan_last_fft_area(const sb_plan* plan);
 /* per-kernel device time (CUDA events on the plan's stream) accumulated while the option
  * "profile" is 1: ms[6], launches[6] in the order k_curv_rows, k_curv_cols, k_tmpl_rows,
  * k_tmpl_sums, k_conv_cols, k_fit_rows.  reset != 0 clears the counters afterwards. */
 int sb_plan_profile(sb_plan* plan, double* ms6, long* launches6, int reset);
 /* number of kernels launched by this plan so far */
 long sb_plan_launch_count(const sb_plan* plan);
-/* FFT domain and tile grid chosen by the last sweep: out[0..5] = Py, Px, tiles_y, tiles_x, angle batch, template batch */
+/* FFT domain and tile grid chosen by the last sweep: out[0..5] = largest Py, largest Px, tiles_y, tiles_x,
+ * angle batch, template batch (tiles of different lengths are mixed along an axis when that wastes less) */
 int sb_plan_last_geometry(const sb_plan* plan, int* out6);
 
 /* DEM upload (DEMGrid._griddata, float64 row-major ny x nx) and the centred axis
@@ -125,8 +151,21 @@ int sb_sweep(sb_plan* plan, const sb_angle* angles, int n_angles,
 int sb_finalize(sb_plan* plan, const double* age_of_host, const double* angle_of_host, int n_idx,
                 double* out4, int out_is_device);
 
-/* Raw best state for a cross-GPU merge: device pointers into the plan, ny*nx each. */
+/* The same for best state `state` and raster rows row_lo .. row_hi - 1 only:
+ * out4 is float64[4 * (row_hi - row_lo) * nx]. */
+int sb_finalize_ex(sb_plan* plan, int state, int row_lo, int row_hi, const double* age_of_host,
+                   const double* angle_of_host, int n_idx, double* out4, int out_is_device);
+
+/* Raw best state for a cross-GPU merge: device pointers into the plan, one value per pixel of
+ * the plan's rows. */
 int sb_best_state(sb_plan* plan, float** snr_dev, float** amp_dev, int32_t** idx_dev);
+int sb_best_state_ex(sb_plan* plan, int state, float** snr_dev, float** amp_dev, int32_t** idx_dev);
+
+/* Fold n_cands candidate best states for raster rows row_lo .. row_hi - 1 (device buffers laid out
+ * [candidate][row][nx], e.g. what an all-to-all of the ranks' best states delivers) into best
+ * state `state`: highest SNR, then lowest flat index; a NaN SNR sticks (core.py:230-240). */
+int sb_best_merge(sb_plan* plan, int state, int row_lo, int row_hi, int n_cands, const float* snr_c,
+                  const float* amp_c, const int32_t* idx_c);
 
 /* Cross-GPU merge of best states (the parent-side reduce over Pool results,
  * core.py:185, when the search is sharded over ranks).  All buffers are device memory
@@ -143,6 +182,19 @@ int sb_best_unpack(sb_plan* plan, const unsigned long long* gkeys_dev, const flo
  * NULL, in which case the scalars age_s / angle_s are used. */
 int sb_compare_host(sb_plan* plan, double* best4_host, const double* amp, const double* age,
                     const double* angle, const double* snr, double age_s, double angle_s);
+
+/* DEMGrid._estimate_curvature_noiselevel (dem.py:152-179): sums, over the pixels whose Gaussian
+ * window (sigma, truncate as scipy.ndimage.gaussian_filter) holds no NaN, of the high-passed second
+ * differences h = d - lowpass(d) and their products -- out10 = [count, hxx, hxy, hyy, hxx^2, hxy^2,
+ * hyy^2, hxx hxy, hxx hyy, hxy hyy].  The directional curvature is linear in (dxx, dxy, dyy)
+ * (dem.py:103-104), so mean and standard deviation for every direction follow from these. */
+int sb_curvature_noise_moments(sb_plan* plan, double sigma, double truncate, double* out10_host);
+
+/* One pass of nodata filling in place of rasterio.fill.fillnodata (dem.py:406-408): NaN cells of
+ * the host raster (ny x nx float64) become the inverse-distance-weighted mean of the nearest valid
+ * cell along the eight row / column / diagonal rays within max_search_distance cells;
+ * *remaining = cells still NaN. */
+int sb_fill_nodata(sb_plan* plan, double* dem_host_inout, double max_search_distance, long* remaining);
 
 /* unit-test hook: batched complex64 FFT of length n (power of two, 64..8192) over rows */
 int sb_debug_fft(sb_plan* plan, int n, int rows, const float* in_host, float* out_host, int inverse);

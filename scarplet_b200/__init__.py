@@ -8,9 +8,10 @@ Drop-in for the reference's ``import scarplet as sl`` on that path::
 """
 from .core import (calculate_best_fit_parameters,  # noqa: F401
                    calculate_best_fit_parameters_serial, compare, match, match_scales,
-                   match_template)
+                   match_template, release)
 from .dem import DEMGrid  # noqa: F401
 from .engine import configure  # noqa: F401
+from .geotiff import write_results as save_results  # noqa: F401
 from . import WindowedTemplate  # noqa: F401
 
 __version__ = "0.1.0"

@@ -28,7 +28,8 @@ class SbTemplate(Structure):
                 ("sx_lo", c_int32), ("sx_hi", c_int32),
                 ("i_lo", c_int32), ("i_hi", c_int32),
                 ("j_lo", c_int32), ("j_hi", c_int32),
-                ("angle_id", c_int32), ("idx", c_int32)]
+                ("angle_id", c_int32), ("idx", c_int32),
+                ("state", c_int32), ("reserved", c_int32)]
 
 
 class SbError(RuntimeError):
@@ -49,6 +50,21 @@ def _declare(lib):
     lib.sb_plan_set_option.argtypes = [P, c_char_p, c_long]
     lib.sb_plan_launch_count.argtypes = [P]
     lib.sb_plan_launch_count.restype = c_long
+    lib.sb_plan_device_bytes.argtypes = [P]
+    lib.sb_plan_device_bytes.restype = c_long
+    lib.sb_plan_last_fft_area.argtypes = [P]
+    lib.sb_plan_last_fft_area.restype = c_double
+    lib.sb_plan_stream.argtypes = [P]
+    lib.sb_plan_stream.restype = c_void_p
+    lib.sb_plan_set_slab.argtypes = [P, c_int, c_int, c_int]
+    lib.sb_plan_dem_rows.argtypes = [P, POINTER(c_int), POINTER(c_int)]
+    lib.sb_plan_curv_stats.argtypes = [P, dp, dp]
+    lib.sb_plan_set_curv_stats.argtypes = [P, c_double, c_double]
+    lib.sb_finalize_ex.argtypes = [P, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int]
+    lib.sb_best_state_ex.argtypes = [P, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
+    lib.sb_best_merge.argtypes = [P, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.sb_curvature_noise_moments.argtypes = [P, c_double, c_double, dp]
+    lib.sb_fill_nodata.argtypes = [P, c_void_p, c_double, POINTER(c_long)]
     lib.sb_plan_last_geometry.argtypes = [P, POINTER(c_int)]
     lib.sb_plan_profile.argtypes = [P, POINTER(c_double), POINTER(c_long), c_int]
     lib.sb_set_dem_host.argtypes = [P, c_void_p]
@@ -76,7 +92,9 @@ def _declare(lib):
                  "sb_set_axes_host", "sb_directional_laplacian", "sb_render_template",
                  "sb_match_template", "sb_match_template_raster", "sb_best_reset", "sb_sweep", "sb_finalize",
                  "sb_best_state", "sb_best_pack", "sb_best_select", "sb_best_unpack",
-                 "sb_compare_host", "sb_debug_fft", "sb_sync"):
+                 "sb_compare_host", "sb_debug_fft", "sb_sync", "sb_plan_set_slab", "sb_plan_dem_rows",
+                 "sb_plan_curv_stats", "sb_plan_set_curv_stats", "sb_finalize_ex", "sb_best_state_ex",
+                 "sb_best_merge", "sb_curvature_noise_moments", "sb_fill_nodata"):
         getattr(lib, name).restype = c_int
     return lib
 
@@ -87,7 +105,10 @@ EXPORTED = ("sb_last_error", "sb_build_info", "sb_plan_create", "sb_plan_destroy
             "sb_directional_laplacian", "sb_render_template", "sb_match_template",
             "sb_match_template_raster", "sb_best_reset", "sb_sweep", "sb_finalize", "sb_best_state", "sb_best_pack",
             "sb_best_select", "sb_best_unpack", "sb_compare_host",
-            "sb_debug_fft", "sb_sync")
+            "sb_debug_fft", "sb_sync", "sb_plan_set_slab", "sb_plan_dem_rows", "sb_plan_curv_stats",
+            "sb_plan_set_curv_stats", "sb_plan_stream", "sb_plan_device_bytes", "sb_plan_last_fft_area",
+            "sb_finalize_ex", "sb_best_state_ex", "sb_best_merge", "sb_curvature_noise_moments",
+            "sb_fill_nodata")
 
 
 def library_path():

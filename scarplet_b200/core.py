@@ -10,9 +10,16 @@ reference; the work is done by the CUDA library behind ``engine.Plan``:
 * the serial ``compare`` fold (core.py:227-241) runs in registers inside the last
   kernel (first maximum wins; see DESIGN.md for the one documented difference on
   exact float64 ties).
+
+Plans (device workspace, twiddle tables, page-locked result buffers) are cached per raster
+geometry, so that a second ``match`` on a raster of the same shape pays for nothing but the
+DEM upload, the search and the result download; ``release()`` frees them.
 """
+import threading
+
 import numpy as np
 
+from . import engine
 from . import params as P
 from .engine import Plan
 from .templates import device_spec
@@ -23,14 +30,69 @@ def _grid_fields(data):
     return z, data._georef_info.dx, data._georef_info.dy
 
 
-def _plan_for(data, **plan_kwargs):
+# ---------------------------------------------------------------------------
+# plan cache
+# ---------------------------------------------------------------------------
+_CACHE_SLOTS = 2
+_cache = []                      # [(key, plan)], most recently used last
+_cache_lock = threading.Lock()
+
+
+class _Lease(object):
+    """A cached plan taken out for one call (context manager: goes back on exit)."""
+
+    def __init__(self, key, plan):
+        self.key, self.plan = key, plan
+
+    def __enter__(self):
+        return self.plan
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is not None:        # a failed call leaves no half-used plan behind
+            self.plan.close()
+            return False
+        with _cache_lock:
+            _cache.append((self.key, self.plan))
+            while len(_cache) > _CACHE_SLOTS:
+                _cache.pop(0)[1].close()
+        return False
+
+
+def _plan_for(data, states=1):
+    """A plan for ``data``'s geometry with its DEM uploaded, out of the cache when one is
+    free (a plan is used by one call at a time: concurrent callers get their own)."""
     z, dx, dy = _grid_fields(data)
     ny, nx = z.shape
-    plan = Plan(ny, nx, dx, dy, **plan_kwargs)
-    plan.set_dem(z)
-    return plan
+    d = engine.DEFAULTS
+    key = (ny, nx, float(dx), float(dy), d["precision"], d["workspace_mb"], d["max_fft"])
+    plan = None
+    with _cache_lock:
+        for i, (k, p) in enumerate(_cache):
+            if k == key:
+                plan = _cache.pop(i)[1]
+                break
+    if plan is None:
+        plan = Plan(ny, nx, dx, dy)
+    try:
+        if plan.states != states:
+            plan.set_states(states)
+        plan.set_dem(z)
+    except Exception:
+        plan.close()
+        raise
+    return _Lease(key, plan)
 
 
+def release():
+    """Free the cached plans (device workspace and page-locked result buffers)."""
+    with _cache_lock:
+        while _cache:
+            _cache.pop()[1].close()
+
+
+# ---------------------------------------------------------------------------
+# plugin templates (classes without an on-device generator)
+# ---------------------------------------------------------------------------
 def _plugin_match_template(plan, data, Template, scale, age, angle, **kwargs):
     """core.py:339-375 for a template class without an on-device generator -- the plugin
     surface: the class is instantiated and asked for its raster and masks exactly as the
@@ -75,10 +137,15 @@ def _plugin_sweep(data, Template, scale, ages, ang_max, ang_min, order, **kwargs
         return outer
 
 
+# ---------------------------------------------------------------------------
+# the reference API
+# ---------------------------------------------------------------------------
 def match_template(data, Template, scale, age, angle, **kwargs):
     """Fit one (scale, age, angle) template to the directional curvature
-    (core.py:297-377).  Returns ``(amp, age, angle, snr)`` with float64 planes."""
-    spec = device_spec(Template)
+    (core.py:297-377).  Returns ``(amp, age, angle, snr)`` with float64 planes.  Extra
+    keyword arguments go to the template's constructor like the reference's (core.py:345);
+    a class that takes any is served through its own ``template()``."""
+    spec = None if kwargs else device_spec(Template)
     with _plan_for(data) as plan:
         if spec is None:
             amp, snr = _plugin_match_template(plan, data, Template, scale, age, angle, **kwargs)
@@ -87,37 +154,47 @@ def match_template(data, Template, scale, age, angle, **kwargs):
     return amp, age, angle, snr
 
 
-def _sweep(data, Template, scale, ages, ang_max, ang_min, order, plan=None):
-    spec = device_spec(Template)
+def _sweep(data, Template, scales, ages, ang_max, ang_min, order, **kwargs):
+    """One search per entry of ``scales`` in a single device sweep (they share each
+    orientation's curvature spectra); returns the list of (4, ny, nx) stacks."""
+    spec = None if kwargs else device_spec(Template)
     if spec is None:
-        return _plugin_sweep(data, Template, scale, ages, ang_max, ang_min, order)
+        return [_plugin_sweep(data, Template, s, ages, ang_max, ang_min, order, **kwargs) for s in scales]
     angles = P.search_angles(ang_min, ang_max)
-    own = plan is None
-    if own:
-        plan = _plan_for(data)
-    try:
-        a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, scale, ages, angles, order)
+    with _plan_for(data, states=len(scales)) as plan:
+        a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, list(scales), ages, angles, order)
         plan.reset()
         plan.sweep(a_rec, t_rec)
-        return plan.finalize(age_of, angle_of)
-    finally:
-        if own:
-            plan.close()
+        return [plan.finalize(age_of, angle_of, state=k) for k in range(len(scales))]
 
 
 def calculate_best_fit_parameters(dem, Template, scale, age, ang_max=np.pi / 2,
                                   ang_min=-np.pi / 2, **kwargs):
     """Best amplitude / orientation / SNR at one age over a 1-degree orientation
-    search (core.py:139-195).  Returns ndarray (4, ny, nx): [amp, age, angle, snr]."""
-    return _sweep(dem, Template, scale, [age], ang_max, ang_min, "age_major")
+    search (core.py:139-195).  Returns ndarray (4, ny, nx): [amp, age, angle, snr].
+    Like the reference (core.py:182) further keyword arguments are accepted and not
+    forwarded to the template."""
+    return _sweep(dem, Template, [scale], [age], ang_max, ang_min, "age_major")[0]
 
 
 def calculate_best_fit_parameters_serial(dem, Template, scale, ang_max=np.pi / 2,
                                          ang_min=-np.pi / 2, **kwargs):
-    """Flat search over orientations x the 35 default ages (core.py:65-136).
+    """Flat search over orientations x the 35 default ages (core.py:65-136); keyword
+    arguments are forwarded to the template's constructor (core.py:116-121).
     Returns ``(best_amp, best_age, best_angle, best_snr)``."""
-    out = _sweep(dem, Template, scale, P.default_ages(), ang_max, ang_min, "angle_major")
+    out = _sweep(dem, Template, [scale], P.default_ages(), ang_max, ang_min, "angle_major", **kwargs)[0]
     return out[0], out[1], out[2], out[3]
+
+
+def _match_args(kwargs):
+    ang_max = kwargs.get('ang_max', np.pi / 2)
+    ang_min = kwargs.get('ang_min', -np.pi / 2)
+    if 'age' in kwargs:
+        return [kwargs['age']], ang_max, ang_min, True
+    # extension: ``ages=`` replaces the hard-coded 35-age grid of core.py:286
+    ages = kwargs.get('ages', None)
+    ages = P.default_ages() if ages is None else np.asarray(ages, dtype=np.float64)
+    return ages, ang_max, ang_min, False
 
 
 def match(data, Template, **kwargs):
@@ -126,41 +203,22 @@ def match(data, Template, **kwargs):
     ``compare`` as a tuple of four planes."""
     if 'age' in kwargs:
         return calculate_best_fit_parameters(data, Template, **kwargs)
-    scale = kwargs['scale']
-    ang_max = kwargs.get('ang_max', np.pi / 2)
-    ang_min = kwargs.get('ang_min', -np.pi / 2)
-    # extension: ``ages=`` replaces the hard-coded 35-age grid of core.py:286
-    ages = kwargs.get('ages', None)
-    ages = P.default_ages() if ages is None else np.asarray(ages, dtype=np.float64)
-    out = _sweep(data, Template, scale, ages, ang_max, ang_min, "age_major")
+    ages, ang_max, ang_min, _ = _match_args(kwargs)
+    out = _sweep(data, Template, [kwargs['scale']], ages, ang_max, ang_min, "age_major")[0]
     return out[0], out[1], out[2], out[3]
 
 
 def match_scales(data, Template, scales, **kwargs):
     """One ``match`` result per template scale -- the multi-scale product the reference
     publishes as one 4-band raster per scale (CHANGELOG.md:20-24), which its users obtain by
-    calling ``match`` in a loop (core.py:266-294 per scale).  The DEM is uploaded and its
-    second differences are built once; every scale is its own search with its own best state.
-    Returns ``{scale: result}`` with ``result`` exactly what ``match(..., scale=scale)`` returns."""
-    spec = device_spec(Template)
-    out = {}
-    if spec is None:
-        for scale in scales:
-            out[scale] = match(data, Template, scale=scale, **kwargs)
-        return out
-    ang_max = kwargs.get('ang_max', np.pi / 2)
-    ang_min = kwargs.get('ang_min', -np.pi / 2)
-    with _plan_for(data) as plan:
-        for scale in scales:
-            if 'age' in kwargs:
-                out[scale] = _sweep(data, Template, scale, [kwargs['age']], ang_max, ang_min,
-                                    "age_major", plan=plan)
-            else:
-                ages = kwargs.get('ages', None)
-                ages = P.default_ages() if ages is None else np.asarray(ages, dtype=np.float64)
-                res = _sweep(data, Template, scale, ages, ang_max, ang_min, "age_major", plan=plan)
-                out[scale] = (res[0], res[1], res[2], res[3])
-    return out
+    calling ``match`` in a loop (core.py:266-294 per scale).  Here all scales run in ONE
+    device sweep: an orientation's curvature spectra are built once and every scale folds
+    into its own best state.  Returns ``{scale: result}`` with ``result`` exactly what
+    ``match(..., scale=scale)`` returns."""
+    scales = list(scales)
+    ages, ang_max, ang_min, single = _match_args(kwargs)
+    res = _sweep(data, Template, scales, ages, ang_max, ang_min, "age_major")
+    return {s: (r if single else (r[0], r[1], r[2], r[3])) for s, r in zip(scales, res)}
 
 
 def compare(results, ny, nx):

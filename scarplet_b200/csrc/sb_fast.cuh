@@ -357,13 +357,11 @@ k_conv_cols_p(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int
 }
 
 // ---------------------------------------------------------------------------
-// k_fit_rows_f<Px>: grid (ceil(out_ny / GP)); every CTA walks the batch of templates
-// two at a time.  Per template and row: Hermitian-extended inverse row FFT of
-// Gt + i Gm (real part xcorr, imaginary part T3), amplitude / SNR (core.py:360-367),
-// edge mask (core.py:373-375), running best-SNR select (core.py:198-243) in
-// registers; the best state is read and written once per launch.
-// Templates with get_err_mask (core.py:369-371) and the raw-plane mode of
-// match_template use k_fit_rows.
+// Fit kernel (complex64 fast path).  Per template and row: Hermitian-extended inverse row
+// FFT of Gt + i Gm (real part xcorr, imaginary part T3), amplitude / SNR (core.py:360-367),
+// edge mask (core.py:373-375), optional get_err_mask (core.py:369-371), running best-SNR
+// select (core.py:198-243) in registers.  The raw-plane mode of match_template and the
+// complex128 pipeline use k_fit_rows (sb_kernels.cuh).
 // ---------------------------------------------------------------------------
 constexpr int kFitMaxBatch = 64;
 
@@ -382,241 +380,12 @@ SB_DEVICE void fit_pixel_fast(float X, float T, const FitT& k, float& amp, float
     snr = fabsf(sb_fdiv_fast(t1, err));              // core.py:367
 }
 
-template <int N, bool PAIRED>
-struct FitCtx {
-    static constexpr int K = sbfft::num_stages(N);
-    static constexpr int T = N / E;
-    static constexpr int LOG2T = ilog2(T);
-    int t;
-    float2 *smA, *smB;
-    const float2* tw;
-    const float4 *rowA, *rowB;        // gbuf rows (nullptr: nothing to do for this stream)
-    const FitT* s_fit;                // shared-memory copies of the batch's scalars
-    int slotA, slotB;                 // batch slots of the two templates in flight
-    int gi, ox, m0;                   // raster row, tile origin, t + dlx
-    int out_nx, nx;
-    bool row_active;
-    int dbg;
-    const int* best_idx;
-    // running best per pixel: SNR, amplitude, and (one byte each) the batch slot of the
-    // template that set them -- kNoSlot while the value read from the best state stands
-    float (&bs)[E];
-    float (&ba)[E];
-    unsigned (&bw)[E / 4];
-    static constexpr unsigned kNoSlot = 0xFFu;
-
-    SB_DEVICE FitCtx(float (&s)[E], float (&a)[E], unsigned (&w)[E / 4]) : bs(s), ba(a), bw(w) {}
-
-    SB_DEVICE void bar() const { sb_sync(); }
-    SB_DEVICE unsigned slot_of(int q) const { return (bw[q >> 2] >> (8 * (q & 3))) & 0xFFu; }
-    // word with byte `b` replaced by `slot`
-    SB_DEVICE static unsigned with_slot(unsigned word, int b, unsigned slot) {
-        return (word & ~(0xFFu << (8 * b))) | (slot << (8 * b));
-    }
-    // flat index behind the current best of element q (rare path: exact SNR ties only)
-    SB_DEVICE int current_idx(int q) const {
-        const unsigned s = slot_of(q);
-        if (s != kNoSlot) return s_fit[s].idx;
-        const int jo = (m0 + q * T) & (N - 1);
-        return best_idx[(long)gi * nx + ox + jo];
-    }
-
-    template <int P> SB_DEVICE void twid(float2 (&w)[TW]) {
-        if (SB_DBG_ON(dbg, 32)) {
-#pragma unroll
-            for (int i = 0; i < TW; ++i) w[i] = make_float2(0.6f, 0.8f);
-            return;
-        }
-        sbfft::load_tw<N, P, float, true>(w, t, tw);      // tw: the CTA's shared-memory copy
-    }
-
-    // bit q set <=> column t + q*T of this row lies inside the template's window
-    SB_DEVICE unsigned mask(const FitT& k) const {
-        if (!row_active || gi < k.i_lo || gi > k.i_hi) return 0u;
-        const int lo = max(k.j_lo - ox, 0), hi = min(k.j_hi - ox, out_nx - 1);
-        const int qlo = max((lo - m0 + T - 1) >> LOG2T, 0);
-        const int qhi = min((hi - m0) >> LOG2T, E - 1);
-        return qlo <= qhi ? ((2u << qhi) - (1u << qlo)) : 0u;
-    }
-
-    template <int P, int F> SB_DEVICE void phase(float2 (&v)[E], const float2 (&w)[TW]) {
-        if constexpr (P == 0) {
-            // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
-            const float4* row = F == 0 ? rowA : rowB;
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool direct = q < E / 2;
-                int kk = q < E / 2 ? t + q * T : N - (t + q * T);
-                if (q == E / 2) { direct = t == 0; kk = direct ? N / 2 : N / 2 - t; }
-                // PAIRED: the CTA's other row group reads the other half of each sector
-                if (row) g4 = SB_DBG_ON(dbg, 16) ? make_float4(1.f, 2.f, 3.f, (float)q)
-                              : PAIRED ? sb_ld_shared_soon(row + kGbufRows * kk) : sb_ld_stream(row + kGbufRows * kk);
-                v[q] = direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
-            }
-        }
-        sbfft::stage_math<N, P, float>(v, w);
-        if constexpr (P == K - 1) {
-            if ((F == 0 ? rowA : rowB) != nullptr) {
-                const unsigned slot = F == 0 ? slotA : slotB;
-                const FitT k = s_fit[slot];
-                if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
-                const unsigned mk = mask(k);
-                // first maximum wins (core.py:230-240).  The select is branch-free; equal
-                // positive SNRs (in float32 mostly the -90 / +90 degree pair) are rare and
-                // resolved afterwards to the lower flat index, so that the result does not
-                // depend on the batch order.
-                unsigned ties = 0u;
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    float amp, snr;
-                    fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
-                    snr = ((mk >> q) & 1u) ? snr : -1.f;          // edge-masked: never wins
-                    const bool take = snr > bs[q];
-                    ties |= (snr == bs[q] && snr > 0.f) ? (1u << q) : 0u;
-                    bs[q] = take ? snr : bs[q];
-                    ba[q] = take ? amp : ba[q];
-                    bw[q >> 2] = take ? with_slot(bw[q >> 2], q & 3, slot) : bw[q >> 2];
-                }
-                if (ties != 0u) {
-#pragma unroll
-                    for (int q = 0; q < E; ++q) {
-                        if (((ties >> q) & 1u) && k.idx < current_idx(q)) {
-                            float amp, snr;
-                            fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
-                            ba[q] = amp;
-                            bw[q >> 2] = with_slot(bw[q >> 2], q & 3, slot);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
-        sbfft::stage_store<N, P, float>(v, t, F == 0 ? smA : smB);
-    }
-    template <int F> SB_DEVICE void load(float2 (&v)[E]) { sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB); }
-};
-
-// MINT: threads per CTA when one row needs fewer.  512 puts the two rows that share every
-// 32-byte sector of the interleaved planes into the same CTA.
-template <int N, int MINT>
-SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > MINT ? N / E : MINT), ((N / E > MINT ? N / E : MINT) > 256 ? 1 : 2))
-k_fit_rows_f(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RESTRICT gbuf,
-             float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
-             const float2* SB_RESTRICT tw) {
-    constexpr int T = N / E;
-    constexpr int THREADS = T > MINT ? T : MINT;
-    constexpr int GP = THREADS / T;
-    constexpr int PL = sbfft::padded_len(N);
-    typedef FitCtx<N, (GP > 1)> Ctx;
-    const int grp = sb_tid() / T, t = sb_tid() % T;
-    float2* sm = (float2*)sb_shared();
-    FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
-    // [kFitMaxBatch] active templates, [kFitMaxBatch] flags (16-byte aligned: the compiler reads
-    // them with vector loads), then the count -- s_list[2 * kFitMaxBatch]
-    int* s_list = (int*)(s_fit + kFitMaxBatch);
-    int* s_flag = s_list + kFitMaxBatch;
-    // the twiddle table next to the data: 30 table reads per thread and template would
-    // otherwise compete with the streamed planes for L1 and mostly come back from L2
-    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 2);
-    sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), THREADS);
-    const int io = sb_bx() * GP + grp;
-    const bool active = io < g.out_ny;
-    const int gi = g.oy + io;
-    const int cta_lo = g.oy + sb_bx() * GP;
-    const int cta_hi = min(cta_lo + GP - 1, g.oy + g.out_ny - 1);
-
-    // stage the batch's scalars; list the templates whose window meets this CTA's rows
-    if (sb_tid() < count) {
-        const FitT k = fit[sb_tid()];
-        s_fit[sb_tid()] = k;
-        s_flag[sb_tid()] = !(cta_hi < k.i_lo || cta_lo > k.i_hi);
-    }
-    sb_sync();
-    if (sb_tid() < count) {
-        int pos = 0;
-        for (int i = 0; i < sb_tid(); ++i) pos += s_flag[i];
-        if (s_flag[sb_tid()]) s_list[pos] = sb_tid();
-        if (sb_tid() == count - 1) s_list[2 * kFitMaxBatch] = pos + s_flag[sb_tid()];
-    }
-    sb_sync();
-    const int n_act = s_list[2 * kFitMaxBatch];
-
-    float bs[E], ba[E];
-    unsigned bw[E / 4];
-    Ctx c(bs, ba, bw);
-    c.t = t;
-    c.smA = sm + (long)grp * 2 * PL;
-    c.smB = c.smA + PL;
-    c.tw = tw_s;
-    c.gi = gi;
-    c.ox = g.ox;
-    c.m0 = t + g.dlx;
-    c.out_nx = g.out_nx;
-    c.nx = g.nx;
-    c.row_active = active;
-    c.dbg = g.dbg;
-    c.s_fit = s_fit;
-    c.best_idx = best_idx;
-#pragma unroll
-    for (int q = 0; q < E / 4; ++q) bw[q] = 0xFFFFFFFFu;
-#pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int jo = (t + q * T + g.dlx) & (N - 1);
-        bs[q] = 0.f; ba[q] = 0.f;
-        if (active && jo < g.out_nx) {
-            const long o = (long)gi * g.nx + g.ox + jo;
-            bs[q] = best_snr[o];
-            ba[q] = best_amp[o];
-        }
-    }
-    // this row's half of its interleaved row pair (gbuf_index)
-    const long row_off = gbuf_index(((active ? io : 0) - g.dly) & (g.Py - 1), 0, g.kpitch);
-    const long tmpl_pitch = (long)g.Py * g.kpitch;
-    const int lines = (g.Px / 2 + 1 + 3) / 4;              // 128-byte lines the row's elements lie in
-
-#pragma unroll 1
-    for (int i = 0; i < n_act; i += 2) {
-        const int pa = s_list[i];
-        const int pb = i + 1 < n_act ? s_list[i + 1] : -1;
-        c.rowA = active ? gbuf + pa * tmpl_pitch + row_off : nullptr;
-        c.rowB = (active && pb >= 0) ? gbuf + pb * tmpl_pitch + row_off : nullptr;
-        c.slotA = pa;
-        c.slotB = pb >= 0 ? pb : pa;
-        if (active && i + 2 < n_act) {                      // next pair's rows towards L2
-            const float4* nx0 = gbuf + s_list[i + 2] * tmpl_pitch + row_off;
-            for (int l = t; l < lines; l += T) sb_prefetch_l2(nx0 + 8 * l);
-            if (i + 3 < n_act) {
-                const float4* nx1 = gbuf + s_list[i + 3] * tmpl_pitch + row_off;
-                for (int l = t; l < lines; l += T) sb_prefetch_l2(nx1 + 8 * l);
-            }
-        }
-        float2 va[E], vb[E];
-        // no barrier between pairs: buffer A was last read before the pair's final barrier,
-        // buffer B is next written after the coming pair's first barrier
-        leapfrog<Ctx::K>(c, va, vb);
-    }
-#pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int jo = (t + q * T + g.dlx) & (N - 1);
-        const unsigned slot = c.slot_of(q);
-        if (active && jo < g.out_nx && slot != Ctx::kNoSlot) {
-            const long o = (long)gi * g.nx + g.ox + jo;
-            best_snr[o] = bs[q];
-            best_amp[o] = ba[q];
-            best_idx[o] = s_fit[slot].idx;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
-// k_fit_rows_g<Px>: row-pair variant of k_fit_rows_f; grid (Py / 2 / GP).  The two transforms
+// k_fit_rows_g<Px>: grid (Py / 2 / GP).  The two transforms
 // a thread group pipelines are the two raster rows that share every 32-byte sector of the
 // interleaved planes (gbuf_index), of ONE template: a thread fetches whole sectors with
 // 256-bit loads and feeds one half to each row, so the planes cross the L2 -> SM crossbar
-// in full sectors (k_fit_rows_f used 16 bytes of every 32 it requested: 4x the algorithmic
-// traffic together with the Hermitian re-read, which here hits L1).  The running best keeps
+// in full sectors (a one-row kernel uses 16 bytes of every 32 it requests).  The running best keeps
 // only the SNR in registers; amplitude and flat index go straight to the best state when a
 // pixel improves (rare after the first templates of a sweep).
 // ---------------------------------------------------------------------------
@@ -636,6 +405,8 @@ struct FitPairCtx {
     int ox, m0, out_nx, nx;
     float* best_amp;
     int* best_idx;
+    const int4* cross;                // get_err_mask column ranges per (angle, raster row), or null
+    int ny;
     int dbg;
     float (&bsA)[E];
     float (&bsB)[E];
@@ -650,7 +421,16 @@ struct FitPairCtx {
 
     SB_DEVICE unsigned mask(const FitT& k, int gi, bool act) const {
         if (!act || gi < k.i_lo || gi > k.i_hi) return 0u;
-        const int lo = max(k.j_lo - ox, 0), hi = min(k.j_hi - ox, out_nx - 1);
+        int jl = k.j_lo, jh = k.j_hi;
+        if (k.errmode != 0) {
+            // snr[get_err_mask()] = 0 (core.py:369-371): a pixel whose SNR is 0 never wins the
+            // fold, so inside a search the mask only narrows the row's candidate columns
+            const int4 cr = cross[(long)k.angle_id * ny + gi];
+            jl = max(jl, k.errmode == 1 ? cr.x : cr.z);
+            jh = min(jh, k.errmode == 1 ? cr.y : cr.w);
+        }
+        const int lo = max(jl - ox, 0), hi = min(jh - ox, out_nx - 1);
+        if (lo > hi) return 0u;
         const int qlo = max((lo - m0 + T - 1) >> LOG2T, 0);
         const int qhi = min((hi - m0) >> LOG2T, E - 1);
         return qlo <= qhi ? ((2u << qhi) - (1u << qlo)) : 0u;
@@ -784,9 +564,14 @@ struct FitPairCtx {
 
 template <int N>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
-k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RESTRICT gbuf,
-             float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
-             const float2* SB_RESTRICT tw) {
+k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RESTRICT fit,
+             const float4* SB_RESTRICT gbuf, float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
+             const float2* SB_RESTRICT tw, const int4* SB_RESTRICT cross) {
+    // `slots` (optional): the `count` batch slots this launch folds -- the templates of one best
+    // state (template scale) inside a batch that mixes several; null: slots 0 .. count - 1.
+    // best_*: the state's planes, offset so that raster row gi is at gi * nx (row slabs).
+    // `cross` (templates with get_err_mask only): per (angle, raster row) the column ranges
+    // with xr > 0 (.x .. .y) and xr < 0 (.z .. .w), k_err_cross.
     constexpr int T = N / E;
     constexpr int THREADS = T > 256 ? T : 256;
     constexpr int GP = THREADS / T;
@@ -796,10 +581,11 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     float2* sm = (float2*)sb_shared();
     FitT* s_fit = (FitT*)(sm + (long)GP * 2 * PL);
     // [kFitMaxBatch] active templates, [kFitMaxBatch] flags (16-byte aligned: the compiler reads
-    // them with vector loads), then the count -- s_list[2 * kFitMaxBatch]
+    // them with vector loads), the count -- s_list[2 * kFitMaxBatch] --, [kFitMaxBatch] gbuf slots
     int* s_list = (int*)(s_fit + kFitMaxBatch);
     int* s_flag = s_list + kFitMaxBatch;
-    float2* tw_s = (float2*)(s_flag + kFitMaxBatch + 2);
+    int* s_gslot = s_flag + kFitMaxBatch + 2;
+    float2* tw_s = (float2*)(s_gslot + kFitMaxBatch);
     sbfft::copy_ctw<N, float>(tw_s, tw, sb_tid(), THREADS);
     const int pairs = g.Py / 2;
     const int pr = min(sb_bx() * GP + grp, pairs - 1);    // row pair of the FFT domain
@@ -809,8 +595,10 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
 
     // stage the batch's scalars; list the templates whose window meets one of this CTA's rows
     if (sb_tid() < count) {
-        const FitT k = fit[sb_tid()];
+        const int slot = slots ? slots[sb_tid()] : sb_tid();
+        const FitT k = fit[slot];
         s_fit[sb_tid()] = k;
+        s_gslot[sb_tid()] = slot;
         int flag = 0;
         for (int r = 0; r < 2 * GP; ++r) {
             const int m = 2 * sb_bx() * GP + r;
@@ -848,6 +636,8 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
     c.dbg = g.dbg;
     c.best_amp = best_amp;
     c.best_idx = best_idx;
+    c.cross = cross;
+    c.ny = g.ny;
 #pragma unroll
     for (int q = 0; q < E; ++q) {
         const int jo = (t + q * T + g.dlx) & (N - 1);
@@ -865,10 +655,10 @@ k_fit_rows_g(Geom g, int count, const FitT* SB_RESTRICT fit, const float4* SB_RE
 #pragma unroll 1
     for (int i = 0; i < n_act; ++i) {
         const int p = s_list[i];
-        c.pair = gbuf + p * tmpl_pitch + row_off;
+        c.pair = gbuf + s_gslot[p] * tmpl_pitch + row_off;
         c.slot = p;
         if (i + 1 < n_act) {                                // next template's row pair towards L2
-            const float4* nx0 = gbuf + s_list[i + 1] * tmpl_pitch + pf_off;
+            const float4* nx0 = gbuf + s_gslot[s_list[i + 1]] * tmpl_pitch + pf_off;
             for (int l = t; l < lines; l += T) sb_prefetch_l2(nx0 + 8 * l);
         }
         // no barrier between templates: buffer A was last read before the final barrier,
@@ -897,6 +687,7 @@ struct CurvCtx {
     const float4* diffs;               // [pixel][dxx, dxy, dyy, -] float32
     float ca2, sc2, sa2;               // cos**2, 2 sin cos, sin**2 of the search angle
     int oy, ox, ny, nx, need_y_lo, need_x_lo, need_x_hi, split_x, poison, dbg;
+    int row0;                          // global raster row of row 0 of `diffs` (row slab; 0 for a whole raster)
     float c2_scale;
     int rp;                            // row pair: rows 2 rp (stream a) and 2 rp + 1 (stream b)
     int need_rows;
@@ -907,7 +698,8 @@ struct CurvCtx {
     template <int F> SB_DEVICE void fill(float2 (&v)[E]) const {
         const int r = 2 * rp + F;
         const bool active = r < need_rows;
-        const int gi = wrap(oy + need_y_lo + (active ? r : 0), ny);
+        int gi = wrap(oy + need_y_lo + (active ? r : 0), ny) - row0;
+        gi += gi < 0 ? ny : 0;                   // row of the slab
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int qx = t + q * T;
@@ -969,6 +761,7 @@ k_curv_rows_f(Geom g, const float4* SB_RESTRICT diffs, const Angle* SB_RESTRICT 
     c.oy = g.oy; c.ox = g.ox; c.ny = g.ny; c.nx = g.nx;
     c.need_y_lo = g.need_y_lo; c.need_x_lo = g.need_x_lo; c.need_x_hi = g.need_x_hi;
     c.split_x = g.split_x; c.poison = g.poison; c.c2_scale = (float)g.c2_scale; c.dbg = g.dbg;
+    c.row0 = g.row0;
     {
         const Angle ang = angles[angle_base + a_loc];
         c.ca2 = (float)ang.ca2;
@@ -1002,13 +795,14 @@ k_curv_rows_f(Geom g, const float4* SB_RESTRICT diffs, const Angle* SB_RESTRICT 
 // pixels inside the windows of the batch's templates are marked here.  A NaN best SNR then
 // loses no later comparison.
 // ---------------------------------------------------------------------------
-SB_GLOBAL k_poison_windows(Geom g, int count, const FitT* SB_RESTRICT fit, float* SB_RESTRICT best_snr) {
+SB_GLOBAL k_poison_windows(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RESTRICT fit,
+                           float* SB_RESTRICT best_snr) {
     const long i = (long)sb_bx() * 256 + sb_tid();
     if (i >= (long)g.out_ny * g.out_nx) return;
     const int gi = g.oy + (int)(i / g.out_nx), gj = g.ox + (int)(i % g.out_nx);
     bool hit = false;
     for (int p = 0; p < count && !hit; ++p) {
-        const FitT k = fit[p];
+        const FitT k = fit[slots ? slots[p] : p];
         hit = gi >= k.i_lo && gi <= k.i_hi && gj >= k.j_lo && gj <= k.j_hi;
     }
     if (hit) best_snr[(long)gi * g.nx + gj] = NAN;

@@ -44,9 +44,19 @@ struct Geom {
     double dx, dx2, dy2;     // cell size, dx**2, dy**2 as the host computes them
     double norm;             // 1 / (Px * Py)
     double c2_scale;         // power of two: curv**2 is packed as curv**2 * c2_scale next to curv
-    int dbg;                 // developer ablation switches (SB_DBG), 0 in production
+    int dbg;                 // developer ablation switches (SB_DBG; builds with -DSB_ABLATE only), else 0
     int poison;              // the DEM holds a NaN: every FFT domain gets one (the reference's fft2 spans the raster)
+    // Row slab (spatial sharding over GPUs): the buffers derived from the DEM hold the
+    // `drows` raster rows starting at global row `row0` (periodic in ny), the best state holds
+    // the rows starting at `brow0`.  A plan over the whole raster has row0 = brow0 = 0, drows = ny.
+    int row0, drows, brow0;
 };
+
+// local row of the DEM-derived buffers for global raster row gi (0 <= gi < ny)
+SB_DEVICE int slab_row(const Geom& g, int gi) {
+    const int li = gi - g.row0;
+    return li < 0 ? li + g.ny : li;
+}
 
 struct Angle {               // one search orientation (curvature direction)
     double ca, sa, ca2, sa2;  // cos, sin, cos**2, sin**2 of the search angle (host float64)
@@ -64,6 +74,8 @@ struct Tmpl {                // one (scale, age, angle) template
     int i_lo, i_hi, j_lo, j_hi;       // un-masked output window (inclusive raster indices)
     int angle_id;            // index into the sweep's angle list
     int idx;                 // flat result index (tie priority and decode key)
+    int state;               // best state the template folds into (one per template scale, CHANGELOG.md:20-24)
+    int reserved;
 };
 
 struct TSum {                // per-template scalars produced by k_tmpl_sums
@@ -75,7 +87,7 @@ struct TSum {                // per-template scalars produced by k_tmpl_sums
 
 constexpr double kEps = 2.220446049250313e-16;   // np.spacing(1), core.py:339
 
-// per-template scalars of the float32 epilogue of k_fit_rows_f (written by k_tmpl_sums)
+// per-template scalars of the float32 epilogue of k_fit_rows_g (written by k_tmpl_sums)
 // xn = norm / tscale and tn = norm / c2_scale are exact powers of two that undo the packing
 // scales and the unnormalised FFTs; they are folded into the constants below (exactly), so
 // the epilogue works on the raw transform outputs X = xcorr / xn, T = T3 / tn.
@@ -86,6 +98,8 @@ struct FitT {
     float inv_n;
     int i_lo, i_hi, j_lo, j_hi;   // un-masked output window (core.py:373-375)
     int idx;                 // flat result index
+    int errmode;             // get_err_mask (core.py:369-371): 0 none, 1 snr = 0 where xr <= 0, 2 where xr >= 0
+    int angle_id;            // row of the k_err_cross table
 };
 
 // gbuf (the inverse-column planes handed from the column kernel to the row kernel) holds,
@@ -128,14 +142,17 @@ SB_DEVICE double zfill(const double* SB_RESTRICT z, long i) {
 // the three angle-independent second differences (dem.py:88-99); NaN centre -> NaN dxx
 struct Diff3 { double dxx, dxy, dyy; };
 
-SB_DEVICE Diff3 second_differences_at(const double* SB_RESTRICT z, int ny, int nx, int i, int j,
-                                      double dx, double dx2, double dy2) {
-    const long o = (long)i * nx + j;
+// gi: raster row (decides the boundary rows of dem.py:90-99); li: the same row's index in `z`,
+// which holds `drows` rows (the whole raster, or a row slab with its halo)
+SB_DEVICE Diff3 second_differences_at(const double* SB_RESTRICT z, int ny, int nx, int gi, int li, int drows,
+                                      int j, double dx, double dx2, double dy2) {
+    const long o = (long)li * nx + j;
     const double zc = sb_ldg(z + o);
     Diff3 r;
     r.dxx = 0.0; r.dyy = 0.0; r.dxy = 0.0;
     if (zc != zc) { r.dxx = zc; return r; }         // dem.py:105
-    const bool jm = j >= 1, jp = j <= nx - 2, im = i >= 1, ip = i <= ny - 2;
+    const bool jm = j >= 1, jp = j <= nx - 2;
+    const bool im = gi >= 1 && li >= 1, ip = gi <= ny - 2 && li <= drows - 2;
     double zl = 0.0, zu = 0.0;
     if (jm) zl = zfill(z, o - 1);
     if (im) zu = zfill(z, o - nx);
@@ -164,9 +181,9 @@ SB_DEVICE double combine_curvature(double dxx, double dxy, double dyy, const Ang
     return sb_add(sb_sub(t0, t1), t2);
 }
 
-SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int i, int j,
+SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int gi, int li, int drows, int j,
                               double dx, double dx2, double dy2, const Angle& a) {
-    const Diff3 d = second_differences_at(z, ny, nx, i, j, dx, dx2, dy2);
+    const Diff3 d = second_differences_at(z, ny, nx, gi, li, drows, j, dx, dx2, dy2);
     if (d.dxx != d.dxx) return d.dxx;
     return combine_curvature(d.dxx, d.dxy, d.dyy, a);
 }
@@ -174,16 +191,22 @@ SB_DEVICE double curvature_at(const double* SB_RESTRICT z, int ny, int nx, int i
 // the DEM's second differences, computed once per DEM: planes [dxx][dxy][dyy] of ny*nx
 // out32: the same three planes rounded to float32, interleaved [pixel][dxx, dxy, dyy, 0], for the
 // complex64 pipeline (its curvature is rounded to float32 before the transform anyway)
-SB_GLOBAL k_second_differences(int ny, int nx, const double* SB_RESTRICT dem, double dx, double dx2,
-                               double dy2, double* SB_RESTRICT out, float4* SB_RESTRICT out32) {
-    const long n = (long)ny * nx;
+// `dem` holds raster rows row0 .. row0 + drows - 1 (mod ny); `out` (optional: complex128 pipeline only)
+SB_GLOBAL k_second_differences(int ny, int nx, int row0, int drows, const double* SB_RESTRICT dem, double dx,
+                               double dx2, double dy2, double* SB_RESTRICT out, float4* SB_RESTRICT out32) {
+    const long n = (long)drows * nx;
     const long i = (long)sb_bx() * 256 + sb_tid();
     if (i >= n) return;
-    const Diff3 d = second_differences_at(dem, ny, nx, (int)(i / nx), (int)(i % nx), dx, dx2, dy2);
-    out[i] = d.dxx;
-    out[n + i] = d.dxy;
-    out[2 * n + i] = d.dyy;
-    out32[i] = make_float4((float)d.dxx, (float)d.dxy, (float)d.dyy, 0.f);
+    const int li = (int)(i / nx);
+    int gi = row0 + li;
+    gi -= gi >= ny ? ny : 0;
+    const Diff3 d = second_differences_at(dem, ny, nx, gi, li, drows, (int)(i % nx), dx, dx2, dy2);
+    if (out) {
+        out[i] = d.dxx;
+        out[n + i] = d.dxy;
+        out[2 * n + i] = d.dyy;
+    }
+    if (out32) out32[i] = make_float4((float)d.dxx, (float)d.dxy, (float)d.dyy, 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -313,7 +336,7 @@ k_curv_rows(Geom g, const double* SB_RESTRICT diffs, const Angle* SB_RESTRICT an
             C2 val = mk2<R>((R)0, (R)0);
             if (active && sx >= g.need_x_lo && sx <= g.need_x_hi) {
                 const int gj = wrap(g.ox + sx, g.nx);
-                const long o = (long)gi * g.nx + gj, n = (long)g.ny * g.nx;
+                const long o = (long)slab_row(g, gi) * g.nx + gj, n = (long)g.drows * g.nx;
                 const double c = combine_curvature(sb_ldg(diffs + o), sb_ldg(diffs + n + o), sb_ldg(diffs + 2 * n + o), ang);
                 val = mk2<R>((R)c, (R)(c * c * g.c2_scale));   // curv, curv**2 (core.py:355)
             }
@@ -515,6 +538,8 @@ SB_GLOBAL k_tmpl_sums(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int 
         k.inv_n = (float)s.inv_n;
         k.i_lo = p.i_lo; k.i_hi = p.i_hi; k.j_lo = p.j_lo; k.j_hi = p.j_hi;
         k.idx = p.idx;
+        k.errmode = p.errmode;
+        k.angle_id = p.angle_id;
         fit[p_loc] = k;
     }
 }
@@ -626,7 +651,7 @@ SB_DEVICE void fit_pixel(float xraw, float traw, const FitScalars& k, float& amp
 
 template <int N, typename R>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), ((N / E > 256 || sizeof(R) == 8) ? 1 : 2))
-k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
+k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count, const int* SB_RESTRICT slots,
            const TSum* SB_RESTRICT sums, const typename Vec<R>::v4* SB_RESTRICT gbuf,
            const double* SB_RESTRICT xvec, const double* SB_RESTRICT yvec, FitOut out,
            const typename Vec<R>::v2* SB_RESTRICT tw) {
@@ -662,7 +687,8 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count,
     const double yv = active ? sb_ldg(yvec + gi) : 0.0;
 
 #pragma unroll 1
-    for (int pl = 0; pl < count; ++pl) {
+    for (int it = 0; it < count; ++it) {
+        const int pl = slots ? slots[it] : it;           // batch slot (one best state's templates)
         const Tmpl p = tmpls[tmpl_base + pl];
         if (!raw && (cta_hi < p.i_lo || cta_lo > p.i_hi)) continue;   // whole CTA edge-masked
         const TSum s = sums[pl];
@@ -762,6 +788,7 @@ SB_GLOBAL k_best_pack(long n, const float* SB_RESTRICT snr, const int* SB_RESTRI
     unsigned int bits;
     const float s = snr[i];
     memcpy(&bits, &s, 4);
+    if (s != s) bits = 0x7FC00000u;        // canonical positive NaN: above every finite SNR as a signed key
     keys[i] = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
 }
 
@@ -773,6 +800,7 @@ SB_GLOBAL k_best_select(long n, const float* SB_RESTRICT snr, const float* SB_RE
     unsigned int bits;
     const float s = snr[i];
     memcpy(&bits, &s, 4);
+    if (s != s) bits = 0x7FC00000u;
     const unsigned long long own =
         ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx[i]);
     amp_out[i] = (own == gkeys[i] && idx[i] != 0x7fffffff) ? amp[i] : 0.f;
@@ -792,15 +820,72 @@ SB_GLOBAL k_best_unpack(long n, const unsigned long long* SB_RESTRICT gkeys,
     amp[i] = amp_in[i];
 }
 
+// get_err_mask of the upper-break templates (WindowedTemplate.py:257-267, 294-304): xr <= 0 or
+// xr >= 0 with xr = x * cos(alpha) + y * sin(alpha) in float64 (WindowedTemplate.py:57).  Along a
+// raster row xr is monotonic in the column (IEEE multiplication and addition are monotonic), so
+// the masks are column ranges: per (search angle, raster row) this kernel finds, by bisection
+// on the exact float64 expression, the inclusive ranges with xr > 0 (.x .. .y) and xr < 0
+// (.z .. .w); empty ranges have lo > hi.  ca / sa: cos / sin of the template's alpha = -angle.
+SB_GLOBAL k_err_cross(int ny, int nx, int n_angles, const double* SB_RESTRICT ca_sa, const double* SB_RESTRICT xvec,
+                      const double* SB_RESTRICT yvec, int4* SB_RESTRICT cross) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= (long)n_angles * ny) return;
+    const int a = (int)(i / ny), row = (int)(i % ny);
+    const double ca = ca_sa[2 * a], sa = ca_sa[2 * a + 1];
+    const double ys = sb_mul(sb_ldg(yvec + row), sa);
+    const bool rising = ca >= 0.0;             // xr does not decrease with the column
+    // first column (in the direction of rising xr) with xr >= 0, and with xr > 0
+    int lo = 0, hi = nx;                       // count of columns with xr < 0
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int j = rising ? mid : nx - 1 - mid;
+        const double xr = sb_add(sb_mul(sb_ldg(xvec + j), ca), ys);
+        if (xr < 0.0) lo = mid + 1; else hi = mid;
+    }
+    const int n_neg = lo;
+    lo = n_neg; hi = nx;                       // count of columns with xr <= 0
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int j = rising ? mid : nx - 1 - mid;
+        const double xr = sb_add(sb_mul(sb_ldg(xvec + j), ca), ys);
+        if (xr <= 0.0) lo = mid + 1; else hi = mid;
+    }
+    const int n_le = lo;
+    int4 r;
+    if (rising) { r.x = n_le; r.y = nx - 1; r.z = 0; r.w = n_neg - 1; }
+    else { r.x = 0; r.y = nx - 1 - n_le; r.z = nx - n_neg; r.w = nx - 1; }
+    cross[i] = r;
+}
+
+// Fold `n_cands` candidate best states (e.g. one per rank of an orientation-sharded search)
+// for the same `n` pixels into one: highest SNR wins, equal SNRs go to the lower flat index
+// (the priority of core.compare's first maximum, core.py:230-240), a NaN SNR sticks
+// (0 * best + 0 * NaN).  Candidate c of pixel i is at [c * n + i].
+SB_GLOBAL k_best_merge(long n, int n_cands, const float* SB_RESTRICT snr_c, const float* SB_RESTRICT amp_c,
+                       const int* SB_RESTRICT idx_c, float* SB_RESTRICT snr, float* SB_RESTRICT amp,
+                       int* SB_RESTRICT idx) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    float bs = snr_c[i], ba = amp_c[i];
+    int bi = idx_c[i];
+    for (int c = 1; c < n_cands; ++c) {
+        const float s = snr_c[(long)c * n + i];
+        const int k = idx_c[(long)c * n + i];
+        if (bs != bs) break;
+        if (s != s || s > bs || (s == bs && k < bi)) { bs = s; ba = amp_c[(long)c * n + i]; bi = k; }
+    }
+    snr[i] = bs; amp[i] = ba; idx[i] = bi;
+}
+
 // decode the best state into the reference's [amp, age, angle, snr] float64 planes
 SB_GLOBAL k_finalize(long n, const float* SB_RESTRICT snr, const float* SB_RESTRICT amp,
                      const int* SB_RESTRICT idx, const double* SB_RESTRICT age_of,
-                     const double* SB_RESTRICT angle_of, double* SB_RESTRICT out4) {
+                     const double* SB_RESTRICT angle_of, int n_idx, double* SB_RESTRICT out4) {
     const long i = (long)sb_bx() * 256 + sb_tid();
     if (i >= n) return;
     const float s = snr[i];
     const int k = idx[i];
-    const bool hit = s > 0.f && k != 0x7fffffff;
+    const bool hit = s > 0.f && k >= 0 && k < n_idx;
     // NaN in the DEM (dem.py:105): compare's select leaves NaN in amp and snr and 0 in age and
     // angle wherever some template was un-masked
     const bool nan = s != s;
@@ -813,18 +898,21 @@ SB_GLOBAL k_finalize(long n, const float* SB_RESTRICT snr, const float* SB_RESTR
 
 // sum over the raster of dxx**2 + dyy**2 (per-block partials, fixed order): gives the
 // curvature scale used to balance curv against curv**2 in the packed FFT
-SB_GLOBAL k_curv_sumsq(int ny, int nx, const double* SB_RESTRICT dem, double dx, double dx2, double dy2,
-                       double* SB_RESTRICT partial) {
+// `dem` holds raster rows row0 .. (slab); the sum runs over its rows own_first .. own_first + own_rows - 1
+SB_GLOBAL k_curv_sumsq(int ny, int nx, int row0, int drows, int own_first, int own_rows,
+                       const double* SB_RESTRICT dem, double dx, double dx2, double dy2, double* SB_RESTRICT partial) {
     double* sd = (double*)sb_shared();
-    const long n = (long)ny * nx;
+    const long n = (long)own_rows * nx;
     Angle a0, a1;
     a0.ca = 1.0; a0.sa = 0.0; a0.ca2 = 1.0; a0.sa2 = 0.0;
     a1.ca = 0.0; a1.sa = 1.0; a1.ca2 = 0.0; a1.sa2 = 1.0;
     double acc = 0.0;
     for (long i = (long)sb_bx() * 256 + sb_tid(); i < n; i += (long)sb_nbx() * 256) {
-        const int r = (int)(i / nx), c = (int)(i % nx);
-        const double u = curvature_at(dem, ny, nx, r, c, dx, dx2, dy2, a0);
-        const double v = curvature_at(dem, ny, nx, r, c, dx, dx2, dy2, a1);
+        const int r = own_first + (int)(i / nx), c = (int)(i % nx);
+        int gr = row0 + r;
+        gr -= gr >= ny ? ny : 0;
+        const double u = curvature_at(dem, ny, nx, gr, r, drows, c, dx, dx2, dy2, a0);
+        const double v = curvature_at(dem, ny, nx, gr, r, drows, c, dx, dx2, dy2, a1);
         acc += u * u + v * v;
     }
     sd[sb_tid()] = acc;
@@ -841,7 +929,8 @@ SB_GLOBAL k_laplacian(int ny, int nx, const double* SB_RESTRICT dem, double dx, 
                       double dy2, Angle a, double* SB_RESTRICT out) {
     const long i = (long)sb_bx() * 256 + sb_tid();
     if (i >= (long)ny * nx) return;
-    out[i] = curvature_at(dem, ny, nx, (int)(i / nx), (int)(i % nx), dx, dx2, dy2, a);
+    const int r = (int)(i / nx);
+    out[i] = curvature_at(dem, ny, nx, r, r, ny, (int)(i % nx), dx, dx2, dy2, a);
 }
 
 // full-raster template in float64 (WindowedTemplate.template())

@@ -11,11 +11,13 @@
 
 #include "sb_kernels.cuh"
 #include "sb_fast.cuh"
+#include "sb_aux.cuh"
 
 static_assert(sizeof(sb_template) == sizeof(sb::Tmpl), "sb_template / sb::Tmpl layout");
 static_assert(sizeof(sb_angle) == sizeof(sb::Angle), "sb_angle / sb::Angle layout");
 static_assert(offsetof(sb_template, kind) == offsetof(sb::Tmpl, kind), "layout");
 static_assert(offsetof(sb_template, idx) == offsetof(sb::Tmpl, idx), "layout");
+static_assert(offsetof(sb_template, state) == offsetof(sb::Tmpl, state), "layout");
 static_assert(offsetof(sb_template, i_lo) == offsetof(sb::Tmpl, i_lo), "layout");
 static_assert(offsetof(sb_template, tscale) == offsetof(sb::Tmpl, tscale), "layout");
 
@@ -48,20 +50,23 @@ struct Buf {
 };
 
 bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
-int next_pow2(long n) {
-    long p = 1;
-    while (p < n) p <<= 1;
-    return (int)p;
-}
 constexpr int kMinFft = 128;
 constexpr int kMaxFftSupported = 8192;
 
+// One FFT tile along an axis: domain length P, first output pixel o, out output pixels.
+struct TileSpec {
+    int P = 0, o = 0, out = 0;
+};
+
 struct AxisPlan {
-    int P = 0;          // FFT length
-    int tiles = 1;
-    int tile_out = 0;   // output pixels per tile (last tile may be shorter)
-    int lo = 0, hi = 0; // support offsets
+    std::vector<TileSpec> tiles;
+    int lo = 0, hi = 0;   // support offsets of the templates along this axis
     bool periodic = false;
+    int max_p() const {
+        int m = 0;
+        for (auto& t : tiles) m = std::max(m, t.P);
+        return m;
+    }
 };
 
 }  // namespace
@@ -72,28 +77,34 @@ struct sb_plan {
     int device = 0;
     sb_stream_t stream = 0;
     bool own_stream = false;
+    // Row slab (spatial sharding): this plan computes raster rows slab_lo .. slab_hi - 1
+    // and holds DEM rows row0 .. row0 + drows - 1 (mod ny).  Whole raster: 0, ny, 0, ny.
+    int slab_lo = 0, slab_hi = 0, row0 = 0, drows = 0;
     double* d_dem = nullptr;
     bool own_dem = false;
-    double* d_diffs = nullptr;      // dxx, dxy, dyy planes of the current DEM (dem.py:88-99)
+    double* d_diffs = nullptr;      // dxx, dxy, dyy planes of the current DEM (dem.py:88-99), complex128 pipeline only
+    bool diffs64_valid = false;
     float4* d_diffs32 = nullptr;    // the same, float32, interleaved per pixel (complex64 pipeline)
     double* d_x = nullptr;
     double* d_y = nullptr;
-    float* d_bsnr = nullptr;
+    int n_states = 1;               // best states (one per template scale in a multi-scale search)
+    float* d_bsnr = nullptr;        // [n_states][slab rows][nx]
     float* d_bamp = nullptr;
     int* d_bidx = nullptr;
     std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
-    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox;
+    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     // persistent column kernel: 1 always, 0 never, -1 (default) when a search angle carries at least
     // four templates -- with fewer, half of its thread groups idle and the per-angle staging of
     // the spectrum columns is not amortised (C2: 94 ms persistent, 69 ms per-template)
-    int conv_persist = std::getenv("SB_CONV_P") ? std::atoi(std::getenv("SB_CONV_P")) : -1;
-    int fit_threads = std::getenv("SB_FIT_THREADS") ? std::atoi(std::getenv("SB_FIT_THREADS")) : 0;
+    int conv_persist = -1;
     long launches = 0;
     double c2_scale = 1.0;
+    double curv_sumsq = 0.0, curv_count = 0.0;   // over the plan's own rows (slab_lo .. slab_hi)
     bool dem_nonfinite = false;    // the DEM holds a NaN / Inf: every FFT domain is poisoned like the reference's
     int profile = 0;
+    int dbg = 0;                   // ablation switches (-DSB_ABLATE builds only)
     std::vector<sb_event_t> ev_pool;
     struct EvPair { int kind; sb_event_t a, b; };
     std::vector<EvPair> ev_live;
@@ -103,7 +114,13 @@ struct sb_plan {
     long workspace_mb = 0;         // 0: half of the free device memory, at most 48 GB
     int max_fft = kMaxFftSupported;
     int force_pad = 0;
+    int mixed_tiles = 1;           // tiles of different FFT lengths along an axis (least wasted area)
     int last_geom[6] = {0, 0, 0, 0, 0, 0};
+    double last_fft_area = 0.0;    // sum over tiles of Py * Px of the last sweep
+
+    long brows() const { return slab_hi - slab_lo; }
+    long bn() const { return brows() * (long)nx; }          // pixels of one best state
+    bool whole() const { return slab_lo == 0 && slab_hi == ny; }
 };
 
 namespace {
@@ -180,11 +197,12 @@ struct Shape {
     static constexpr size_t smem = (size_t)GP * sbfft::padded_len(N) * sizeof(typename Vec<R>::v2);
     // k_conv_cols adds a park buffer of N elements per group
     static constexpr size_t smem_conv = (size_t)GP * (sbfft::padded_len(N) + N) * sizeof(typename Vec<R>::v2);
-    // pipelined kernels (sb_fast.cuh): two exchange buffers per group; k_fit_rows_f adds the
-    // batch's scalars, the active-template list (+ its length) and the flags
+    // pipelined kernels (sb_fast.cuh): two exchange buffers per group; k_fit_rows_g adds the
+    // batch's scalars, the active-template list (+ its length), the flags, the gbuf slots and the
+    // compact twiddle table
     static constexpr size_t smem_conv_f = (size_t)GP * 2 * sbfft::padded_len(N) * sizeof(float2);
     static constexpr size_t smem_fit_f = smem_conv_f + sb::kFitMaxBatch * sizeof(sb::FitT) +
-                                         (2 * sb::kFitMaxBatch + 2) * sizeof(int) +
+                                         (3 * sb::kFitMaxBatch + 2) * sizeof(int) +
                                          (size_t)sbfft::ctw_count<float>(N) * sizeof(float2);
 };
 
@@ -247,83 +265,168 @@ void drain_profile(sb_plan* pl) {
     pl->ev_used = 0;
 }
 
-// curvature RMS -> power-of-two factor that brings curv**2 to the magnitude of curv
-int update_curv_scale(sb_plan* pl) {
-    {   // the angle-independent second differences, once per DEM
-        const long n = (long)pl->ny * pl->nx;
-        if (!pl->d_diffs) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs, (size_t)n * 3 * sizeof(double)));
-        if (!pl->d_diffs32) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs32, (size_t)n * sizeof(float4)));
-        SB_LAUNCH(sb::k_second_differences, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx,
-                  (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, pl->d_diffs, pl->d_diffs32);
-        SB_OK(check_launch(pl, "k_second_differences"));
-    }
-    const int blocks = std::max(1, std::min(1024, div_up((long)pl->ny * pl->nx, 256)));
+// curvature RMS -> power-of-two factor that brings curv**2 to the magnitude of curv; a
+// non-finite sum means a NaN / Inf somewhere in the DEM: it reaches every output pixel through
+// the reference's full-raster fft2 (dem.py:105, core.py:353-363), and tiles or slabs that do
+// not hold the cell have to be told
+void apply_curv_stats(sb_plan* pl, double sumsq, double count) {
+    const double sigma = std::sqrt(sumsq / (2.0 * std::max(count, 1.0)));
+    pl->c2_scale = 1.0;
+    if (std::isfinite(sigma) && sigma > 1e-150 && sigma < 1e150)
+        pl->c2_scale = std::exp2(std::round(-std::log2(sigma)));
+    pl->dem_nonfinite = !std::isfinite(sumsq);
+}
+
+int alloc_best(sb_plan* pl) {
+    for (void* p : {(void*)pl->d_bsnr, (void*)pl->d_bamp, (void*)pl->d_bidx})
+        if (p) sb_rt_free(p);
+    pl->d_bsnr = nullptr; pl->d_bamp = nullptr; pl->d_bidx = nullptr;
+    const size_t n = (size_t)pl->bn() * pl->n_states;
+    int e = 0;
+    e |= sb_rt_malloc((void**)&pl->d_bsnr, n * sizeof(float));
+    e |= sb_rt_malloc((void**)&pl->d_bamp, n * sizeof(float));
+    e |= sb_rt_malloc((void**)&pl->d_bidx, n * sizeof(int));
+    if (e) return fail("out of device memory (best state)");
+    return sb_best_reset(pl);
+}
+
+// angle-independent second differences of the current DEM (once per DEM) and its curvature scale
+int after_dem(sb_plan* pl) {
+    const long n = (long)pl->drows * pl->nx;
+    if (!pl->d_diffs32) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs32, (size_t)n * sizeof(float4)));
+    pl->diffs64_valid = false;
+    SB_LAUNCH(sb::k_second_differences, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx, pl->row0,
+              pl->drows, (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, (double*)nullptr, pl->d_diffs32);
+    SB_OK(check_launch(pl, "k_second_differences"));
+    // statistics over the plan's own rows only, so that the slabs of a sharded raster add up
+    const int own_first = pl->slab_lo - pl->row0 + (pl->slab_lo < pl->row0 ? pl->ny : 0);
+    const long own = pl->brows() * (long)pl->nx;
+    const int blocks = std::max(1, std::min(1024, div_up(own, 256)));
     SB_OK(ensure(pl->raw, (size_t)blocks * sizeof(double)));
-    SB_LAUNCH(sb::k_curv_sumsq, dim3(blocks), dim3(256), 256 * sizeof(double), pl->stream, pl->ny, pl->nx,
-              (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, (double*)pl->raw.p);
+    SB_LAUNCH(sb::k_curv_sumsq, dim3(blocks), dim3(256), 256 * sizeof(double), pl->stream, pl->ny, pl->nx, pl->row0,
+              pl->drows, own_first, (int)pl->brows(), (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2,
+              (double*)pl->raw.p);
     SB_OK(check_launch(pl, "k_curv_sumsq"));
     std::vector<double> part(blocks);
     SB_TRY(sb_rt_d2h(part.data(), pl->raw.p, (size_t)blocks * sizeof(double), pl->stream));
     SB_TRY(sb_rt_sync(pl->stream));
     double sum = 0.0;
     for (double v : part) sum += v;
-    const double sigma = std::sqrt(sum / (2.0 * (double)pl->ny * (double)pl->nx));
-    pl->c2_scale = 1.0;
-    if (std::isfinite(sigma) && sigma > 1e-150 && sigma < 1e150)
-        pl->c2_scale = std::exp2(std::round(-std::log2(sigma)));
-    // a NaN anywhere in the DEM reaches every output pixel through the reference's full-raster
-    // fft2 (dem.py:105, core.py:353-363); tiles that do not hold the cell have to be told
-    pl->dem_nonfinite = !std::isfinite(sum);
+    pl->curv_sumsq = sum;
+    pl->curv_count = (double)own;
+    apply_curv_stats(pl, sum, (double)own);
     return 0;
 }
 
-// choose FFT length / tiling along one axis
-int plan_axis(const sb_plan* pl, int n, int lo, int hi, AxisPlan* ax) {
+int ensure_diffs64(sb_plan* pl) {
+    if (pl->diffs64_valid) return 0;
+    const long n = (long)pl->drows * pl->nx;
+    if (!pl->d_diffs) SB_TRY(sb_rt_malloc((void**)&pl->d_diffs, (size_t)n * 3 * sizeof(double)));
+    SB_LAUNCH(sb::k_second_differences, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx, pl->row0,
+              pl->drows, (const double*)pl->d_dem, pl->dx, pl->dx2, pl->dy2, pl->d_diffs, (float4*)nullptr);
+    SB_OK(check_launch(pl, "k_second_differences"));
+    pl->diffs64_valid = true;
+    return 0;
+}
+
+// relative cost per point of the kernels at FFT length P (4096 is the length they are tuned for;
+// 8192 needs a fourth exchange stage and has no persistent column kernel)
+double length_weight(int P) {
+    switch (P) {
+        case 8192: return 1.25;
+        case 4096: return 1.0;
+        case 2048: return 1.05;
+        case 1024: return 1.12;
+        default: return 1.3;
+    }
+}
+
+// Cover output pixels [r0, r1) of an axis of n pixels with FFT tiles.  A tile of length P
+// yields P - ext output pixels (ext = support extent of the templates along the axis); tiles
+// of different lengths are mixed so that the summed (weighted) FFT length is least -- e.g.
+// 16384 px with a 313 px support: 4 x 4096 + 1 x 2048 = 18432 instead of 5 x 4096 = 20480.
+int plan_axis(const sb_plan* pl, int n, int r0, int r1, int lo, int hi, bool allow_periodic, AxisPlan* ax) {
     lo = std::min(lo, 0);
     hi = std::max(hi, 0);
     ax->lo = lo;
     ax->hi = hi;
+    ax->tiles.clear();
     const int ext = hi - lo + 1;
+    const int len = r1 - r0;
     // complex128 at 8192 would need 270 KB of shared memory per column in k_conv_cols
     const int max_fft = std::min(pl->max_fft, pl->precision == 64 ? 4096 : kMaxFftSupported);
-    if (is_pow2(n) && n >= kMinFft && n <= max_fft && !pl->force_pad) {
-        ax->P = n;
-        ax->tiles = 1;
-        ax->tile_out = n;
+    if (allow_periodic && r0 == 0 && r1 == n && is_pow2(n) && n >= kMinFft && n <= max_fft && !pl->force_pad) {
         ax->periodic = true;
+        TileSpec t;
+        t.P = n; t.o = 0; t.out = n;
+        ax->tiles.push_back(t);
         return 0;
     }
     ax->periodic = false;
-    long best_cost = -1;
+    std::vector<int> Ps;
     for (int P = kMinFft; P <= max_fft; P <<= 1) {
-        if (P < ext + 1 || hi >= P / 2 || -lo > P / 2) continue;
-        const int cap = P - ext;
-        if (cap < 1) continue;
-        const int tiles = div_up(n, cap);
-        const long cost = (long)tiles * P;
-        // equal cost: 4096, the length the pipelined kernels are tuned for, beats 2048
-        if (best_cost < 0 || cost < best_cost || (cost == best_cost && P == 4096)) {
-            best_cost = cost;
-            ax->P = P;
-            ax->tiles = tiles;
-            ax->tile_out = div_up(n, tiles);
-        }
+        if (P < ext + 1 || hi >= P / 2 || -lo > P / 2 || P - ext < 1) continue;
+        Ps.push_back(P);
     }
-    if (best_cost < 0)
+    if (Ps.empty())
         return fail("template support (" + std::to_string(ext) + " px) does not fit max_fft=" +
                     std::to_string(max_fft));
+    std::vector<int> chosen;
+    if (pl->mixed_tiles) {
+        // covering knapsack: best[r] = least cost to cover r more pixels
+        std::vector<double> best(len + 1, 0.0);
+        std::vector<int> pick(len + 1, 0);
+        for (int r = 1; r <= len; ++r) {
+            best[r] = -1.0;
+            for (int P : Ps) {
+                const int cap = P - ext;
+                // a small per-tile charge keeps the count of tiles (launches, halo re-reads) down
+                const double c = P * length_weight(P) + 48.0 + best[std::max(0, r - cap)];
+                if (best[r] < 0 || c < best[r] - 1e-9) { best[r] = c; pick[r] = P; }
+            }
+        }
+        for (int r = len; r > 0; r = std::max(0, r - (pick[r] - ext))) chosen.push_back(pick[r]);
+        std::sort(chosen.begin(), chosen.end(), [](int a, int b) { return a > b; });
+    } else {
+        long best_cost = -1;
+        int bestP = 0, tiles = 0;
+        for (int P : Ps) {
+            const int t = div_up(len, P - ext);
+            const long cost = (long)t * P;
+            // equal cost: 4096, the length the pipelined kernels are tuned for, beats 2048
+            if (best_cost < 0 || cost < best_cost || (cost == best_cost && P == 4096)) { best_cost = cost; bestP = P; tiles = t; }
+        }
+        chosen.assign(tiles, bestP);
+    }
+    // spread the slack over the tiles in proportion to their capacity (equal lengths -> equal tiles)
+    long cap_total = 0;
+    for (int P : chosen) cap_total += P - ext;
+    int o = r0, left = len;
+    long cap_left = cap_total;
+    for (size_t i = 0; i < chosen.size(); ++i) {
+        const int cap = chosen[i] - ext;
+        int out = i + 1 == chosen.size() ? left : (int)std::min<long>(cap, div_up((long)left * cap, cap_left));
+        out = std::min(out, cap);
+        TileSpec t;
+        t.P = chosen[i]; t.o = o; t.out = out;
+        ax->tiles.push_back(t);
+        o += out;
+        left -= out;
+        cap_left -= cap;
+    }
+    if (left != 0) return fail("internal: tile plan does not cover the axis");
     return 0;
 }
 
-void fill_axis(const AxisPlan& ax, int n, int tile, int* o, int* out_n, int* split, int* dl,
-               int* need_lo, int* need_hi) {
+void fill_axis(const AxisPlan& ax, int n, const TileSpec& t, int* o, int* out_n, int* split, int* dl, int* need_lo,
+               int* need_hi) {
     *dl = -(n & 1);
-    *o = tile * ax.tile_out;
-    *out_n = std::min(ax.tile_out, n - *o);
+    *o = t.o;
+    *out_n = t.out;
     if (ax.periodic) {
-        *split = ax.P;
+        *split = t.P;
         *need_lo = 0;
-        *need_hi = ax.P - 1;
+        *need_hi = t.P - 1;
     } else {
         *split = *out_n - *dl - ax.lo + 1;
         *need_lo = -*dl - ax.hi;
@@ -336,25 +439,48 @@ struct SweepOut {
     double* raw_snr = nullptr;
 };
 
+// the templates of one best state inside a chunk (one launch of the column kernel)
+struct SlotGroup {
+    int state = 0;
+    int off = 0;       // offset into the plan's slot table; -1: the whole chunk, in order
+    int count = 0;
+    bool err = false;  // some template of the group has a get_err_mask
+};
+struct Chunk {
+    int pb = 0, cnt = 0;
+    std::vector<SlotGroup> groups;
+};
+struct AngleBatch {
+    int a0 = 0, a1 = 0;
+    std::vector<Chunk> chunks;
+};
+
 template <typename R>
-int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in,
-                int n_tmpls, SweepOut so) {
+int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in, int n_tmpls,
+                SweepOut so) {
     typedef typename Vec<R>::v2 C2;
     typedef typename Vec<R>::v4 C4;
     if (!pl->d_dem) return fail("no DEM set (sb_set_dem_host / sb_set_dem_dev)");
     if (pl->ny < 3 || pl->nx < 3) return fail("raster too small for a template search");
     if (!pl->d_x || !pl->d_y) return fail("no axis vectors set (sb_set_axes_host)");
     if (n_tmpls <= 0 || n_angles <= 0) return 0;
+    if (so.raw_amp && !pl->whole()) return fail("match_template planes need a plan over the whole raster");
+    constexpr bool kF32 = std::is_same<R, float>::value;
+    const bool fast = kF32 && pl->fast;
+    if (!fast) SB_OK(ensure_diffs64(pl));
 
-    // order templates by search angle so that each curvature spectrum is built once
+    // order templates by search angle (then best state) so that each curvature spectrum is built once
     std::vector<sb_template> tm(tmpls_in, tmpls_in + n_tmpls);
-    std::stable_sort(tm.begin(), tm.end(),
-                     [](const sb_template& a, const sb_template& b) { return a.angle_id < b.angle_id; });
+    std::stable_sort(tm.begin(), tm.end(), [](const sb_template& a, const sb_template& b) {
+        return a.angle_id != b.angle_id ? a.angle_id < b.angle_id : a.state < b.state;
+    });
     int lo_y = 0, hi_y = 0, lo_x = 0, hi_x = 0, syp = 1;
+    bool any_err = false, multi_state = false;
     for (auto& t : tm) {
         if (t.kind == SB_KIND_RASTER && (n_tmpls != 1 || !pl->tbox.p))
             return fail("raster templates go through sb_match_template_raster, one at a time");
         if (t.angle_id < 0 || t.angle_id >= n_angles) return fail("template angle_id out of range");
+        if (t.state < 0 || t.state >= pl->n_states) return fail("template state out of range (option \"states\")");
         if (t.sy_hi < t.sy_lo || t.sx_hi < t.sx_lo) return fail("empty template support box");
         if (t.sy_lo < -(pl->ny / 2) || t.sy_hi > pl->ny - 1 - pl->ny / 2 || t.sx_lo < -(pl->nx / 2) ||
             t.sx_hi > pl->nx - 1 - pl->nx / 2)
@@ -364,23 +490,35 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
         lo_x = std::min(lo_x, t.sx_lo);
         hi_x = std::max(hi_x, t.sx_hi);
         syp = std::max(syp, t.sy_hi - t.sy_lo + 1);
+        any_err |= t.errmode != 0;
+        multi_state |= t.state != tm[0].state;
     }
     syp += syp & 1;      // the row kernels store row pairs
     AxisPlan ay, ax;
-    SB_OK(plan_axis(pl, pl->ny, lo_y, hi_y, &ay));
-    SB_OK(plan_axis(pl, pl->nx, lo_x, hi_x, &ax));
-    const int Py = ay.P, Px = ax.P;
-    const int KX = Px / 2 + 1;
-    const int kpitch = Px / 2 + 8;
+    SB_OK(plan_axis(pl, pl->ny, pl->slab_lo, pl->slab_hi, lo_y, hi_y, pl->whole(), &ay));
+    SB_OK(plan_axis(pl, pl->nx, 0, pl->nx, lo_x, hi_x, true, &ax));
+    const int Pym = ay.max_p(), Pxm = ax.max_p();
+    if (!pl->whole()) {
+        // the curvature rows (+ 1 for the stencil) every tile needs must lie inside the slab's halo
+        for (auto& t : ay.tiles) {
+            int o, out_n, split, dl, nlo, nhi;
+            fill_axis(ay, pl->ny, t, &o, &out_n, &split, &dl, &nlo, &nhi);
+            const long first = (long)o + nlo - 1, last = (long)o + nhi + 1;
+            const long have_lo = (long)pl->slab_lo - (pl->slab_lo - pl->row0 + (pl->slab_lo < pl->row0 ? pl->ny : 0));
+            if (pl->drows < pl->ny && (first < have_lo || last >= have_lo + pl->drows))
+                return fail("row slab: halo too small for the template support (need rows " + std::to_string(first) +
+                            ".." + std::to_string(last) + ", have " + std::to_string(have_lo) + ".." +
+                            std::to_string(have_lo + pl->drows - 1) + ")");
+        }
+    }
 
-    const C2 *twy = nullptr, *twx = nullptr;
-    SB_OK(twiddles<R>(pl, Py, &twy));
-    SB_OK(twiddles<R>(pl, Px, &twx));
-
-    // batch sizes from the workspace budget
-    const int need_rows_max = ay.periodic ? Py : std::min(Py, ay.tile_out + (hi_y - lo_y) + 2);
-    const size_t per_angle = (size_t)(need_rows_max + 1) * KX * sizeof(C4) + (size_t)2 * KX * Py * sizeof(C2);
-    const size_t per_tmpl = (size_t)KX * syp * sizeof(C4) + (size_t)Py * kpitch * sizeof(C4) +
+    // batch sizes from the workspace budget (sized for the largest tile)
+    const int KXm = Pxm / 2 + 1;
+    const int kpitch_m = Pxm / 2 + 8;
+    int need_rows_max = 0;
+    for (auto& t : ay.tiles) need_rows_max = std::max(need_rows_max, ay.periodic ? t.P : std::min(t.P, t.out + (hi_y - lo_y) + 2));
+    const size_t per_angle = (size_t)(need_rows_max + 2) * KXm * sizeof(C4) + (size_t)2 * KXm * Pym * sizeof(C2);
+    const size_t per_tmpl = (size_t)KXm * syp * sizeof(C4) + (size_t)Pym * kpitch_m * sizeof(C4) +
                             (size_t)syp * sizeof(double2) + sizeof(sb::TSum);
     size_t budget = (size_t)pl->workspace_mb << 20;
     if (pl->workspace_mb <= 0) {
@@ -404,53 +542,116 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     if (max_per_angle == 1) Bt = std::min(Bt, Ba), Ba = std::min(Ba, Bt);
     Bt = std::min(Bt, n_tmpls);
     // whole angles per batch when they fit: templates of one angle share the curvature spectra
-    if (max_per_angle > 1 && Bt >= max_per_angle) Bt = (Bt / max_per_angle) * max_per_angle;
-    else if (Bt > 1) Bt &= ~1;       // k_fit_rows_f walks the batch two templates at a time
+    if (max_per_angle > 1 && Bt >= max_per_angle) {
+        Bt = (Bt / max_per_angle) * max_per_angle;
+    }
 
     const int rpitch_max = need_rows_max + (need_rows_max & 1);
-    SB_OK(ensure(pl->cr, (size_t)Ba * KX * rpitch_max * sizeof(C4)));
-    SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KX * Py * sizeof(C2)));
-    SB_OK(ensure(pl->trt, (size_t)Bt * KX * syp * sizeof(C4)));
+    SB_OK(ensure(pl->cr, (size_t)Ba * KXm * rpitch_max * sizeof(C4)));
+    SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KXm * Pym * sizeof(C2)));
+    SB_OK(ensure(pl->trt, (size_t)Bt * KXm * syp * sizeof(C4)));
     SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
-    SB_OK(ensure(pl->gbuf, (size_t)Bt * Py * kpitch * sizeof(C4)));
+    SB_OK(ensure(pl->gbuf, (size_t)Bt * Pym * kpitch_m * sizeof(C4)));
     SB_OK(ensure(pl->sums, (size_t)Bt * sizeof(sb::TSum)));
     SB_OK(ensure(pl->fit, (size_t)Bt * sizeof(sb::FitT)));
     SB_OK(ensure(pl->tmpls, (size_t)n_tmpls * sizeof(sb::Tmpl)));
     SB_OK(ensure(pl->angles, (size_t)n_angles * sizeof(sb::Angle)));
+
+    // the schedule: angle batches, chunks of templates, and per chunk the slots of each best state
+    std::vector<AngleBatch> batches;
+    std::vector<int> slot_table;
+    for (int a0 = 0; a0 < n_angles; a0 += Ba) {
+        AngleBatch ab;
+        ab.a0 = a0;
+        ab.a1 = std::min(n_angles, a0 + Ba);
+        const int p0 = first[ab.a0], p1 = first[ab.a1];
+        for (int pb = p0; pb < p1; pb += Bt) {
+            Chunk ch;
+            ch.pb = pb;
+            ch.cnt = std::min(Bt, p1 - pb);
+            std::vector<int> states;
+            for (int i = 0; i < ch.cnt; ++i)
+                if (std::find(states.begin(), states.end(), tm[pb + i].state) == states.end()) states.push_back(tm[pb + i].state);
+            std::sort(states.begin(), states.end());
+            for (int s : states) {
+                // at most kFitMaxBatch slots per launch of the fit kernel
+                SlotGroup gp;
+                gp.state = s;
+                auto flush = [&]() {
+                    if (gp.count == 0) return;
+                    if (states.size() == 1 && gp.count == ch.cnt) { gp.off = -1; slot_table.resize(slot_table.size() - gp.count); }
+                    ch.groups.push_back(gp);
+                    gp.count = 0; gp.err = false;
+                };
+                gp.off = (int)slot_table.size();
+                for (int i = 0; i < ch.cnt; ++i) {
+                    if (tm[pb + i].state != s) continue;
+                    if (gp.count == sb::kFitMaxBatch) { flush(); gp.off = (int)slot_table.size(); }
+                    slot_table.push_back(i);
+                    gp.count++;
+                    gp.err |= tm[pb + i].errmode != 0;
+                }
+                flush();
+            }
+            ab.chunks.push_back(ch);
+        }
+        if (!ab.chunks.empty()) batches.push_back(ab);
+    }
+    SB_OK(ensure(pl->slots, std::max<size_t>(1, slot_table.size()) * sizeof(int)));
+    if (!slot_table.empty())
+        SB_TRY(sb_rt_h2d(pl->slots.p, slot_table.data(), slot_table.size() * sizeof(int), pl->stream));
     SB_TRY(sb_rt_h2d(pl->tmpls.p, tm.data(), (size_t)n_tmpls * sizeof(sb::Tmpl), pl->stream));
     SB_TRY(sb_rt_h2d(pl->angles.p, angles, (size_t)n_angles * sizeof(sb::Angle), pl->stream));
+    std::vector<double> casa;
+    if (any_err && fast && !so.raw_amp) {
+        // get_err_mask column ranges per (angle, raster row): cos / sin of the templates' alpha
+        casa.assign((size_t)2 * n_angles, 0.0);
+        for (auto& t : tm) { casa[2 * t.angle_id] = t.cos_t; casa[2 * t.angle_id + 1] = t.sin_t; }
+        SB_OK(ensure(pl->casa, casa.size() * sizeof(double)));
+        SB_OK(ensure(pl->cross, (size_t)n_angles * pl->ny * sizeof(int4)));
+        SB_TRY(sb_rt_h2d(pl->casa.p, casa.data(), casa.size() * sizeof(double), pl->stream));
+        SB_LAUNCH(sb::k_err_cross, dim3(div_up((long)n_angles * pl->ny, 256)), dim3(256), 0, pl->stream, pl->ny, pl->nx,
+                  n_angles, (const double*)pl->casa.p, (const double*)pl->d_x, (const double*)pl->d_y, (int4*)pl->cross.p);
+        SB_OK(check_launch(pl, "k_err_cross"));
+    }
     // the host vectors must outlive the async copies
     SB_TRY(sb_rt_sync(pl->stream));
 
-    pl->last_geom[0] = Py; pl->last_geom[1] = Px; pl->last_geom[2] = ay.tiles; pl->last_geom[3] = ax.tiles;
-    pl->last_geom[4] = Ba; pl->last_geom[5] = Bt;
+    pl->last_geom[0] = Pym; pl->last_geom[1] = Pxm; pl->last_geom[2] = (int)ay.tiles.size();
+    pl->last_geom[3] = (int)ax.tiles.size(); pl->last_geom[4] = Ba; pl->last_geom[5] = Bt;
+    pl->last_fft_area = 0.0;
 
     const sb::Tmpl* d_tm = (const sb::Tmpl*)pl->tmpls.p;
     const sb::Angle* d_an = (const sb::Angle*)pl->angles.p;
-    sb::FitOut fo;
-    fo.best_snr = pl->d_bsnr; fo.best_amp = pl->d_bamp; fo.best_idx = pl->d_bidx;
-    fo.raw_amp = so.raw_amp; fo.raw_snr = so.raw_snr;
+    const long bn = pl->bn();
+    const long boff = (long)pl->slab_lo * pl->nx;       // best planes are addressed by raster row
 
-    for (int ty = 0; ty < ay.tiles; ++ty)
-        for (int tx = 0; tx < ax.tiles; ++tx) {
+    for (auto& tyS : ay.tiles)
+        for (auto& txS : ax.tiles) {
+            const int Py = tyS.P, Px = txS.P;
+            const int KX = Px / 2 + 1;
+            const int kpitch = Px / 2 + 8;
+            pl->last_fft_area += (double)Py * Px;
+            const C2 *twy = nullptr, *twx = nullptr;
+            SB_OK(twiddles<R>(pl, Py, &twy));
+            SB_OK(twiddles<R>(pl, Px, &twx));
             sb::Geom g;
             g.ny = pl->ny; g.nx = pl->nx; g.Py = Py; g.Px = Px;
-            fill_axis(ay, pl->ny, ty, &g.oy, &g.out_ny, &g.split_y, &g.dly, &g.need_y_lo, &g.need_y_hi);
-            fill_axis(ax, pl->nx, tx, &g.ox, &g.out_nx, &g.split_x, &g.dlx, &g.need_x_lo, &g.need_x_hi);
+            fill_axis(ay, pl->ny, tyS, &g.oy, &g.out_ny, &g.split_y, &g.dly, &g.need_y_lo, &g.need_y_hi);
+            fill_axis(ax, pl->nx, txS, &g.ox, &g.out_nx, &g.split_x, &g.dlx, &g.need_x_lo, &g.need_x_hi);
             g.kpitch = kpitch; g.syp = syp;
             g.dx = pl->dx; g.dx2 = pl->dx2; g.dy2 = pl->dy2;
             g.norm = 1.0 / ((double)Px * (double)Py);
             g.c2_scale = pl->c2_scale;
-            g.dbg = std::getenv("SB_DBG") ? std::atoi(std::getenv("SB_DBG")) : 0;
+            g.dbg = pl->dbg;
             g.poison = pl->dem_nonfinite ? 1 : 0;
+            g.row0 = pl->row0; g.drows = pl->drows; g.brow0 = pl->slab_lo;
             const int need_rows = g.need_y_hi - g.need_y_lo + 1;
             g.rpitch = need_rows + (need_rows & 1);
 
-            for (int a0 = 0; a0 < n_angles; a0 += Ba) {
-                const int a1 = std::min(n_angles, a0 + Ba);
-                const int p0 = first[a0], p1 = first[a1];
-                if (p1 == p0) continue;
-                if (std::is_same<R, float>::value && pl->fast) {
+            for (auto& ab : batches) {
+                const int a0 = ab.a0, a1 = ab.a1;
+                if (fast) {
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, float>;
@@ -483,8 +684,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                               pl->stream, g, (const C4*)pl->cr.p, (C2*)pl->fct.p, twy);
                     return check_launch(pl, "k_curv_cols");
                 }));
-                for (int pb = p0; pb < p1; pb += Bt) {
-                    const int cnt = std::min(Bt, p1 - pb);
+                for (auto& ch : ab.chunks) {
+                    const int pb = ch.pb, cnt = ch.cnt;
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, R>;
@@ -513,11 +714,8 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                   (const double2*)pl->part.p, (sb::TSum*)pl->sums.p, (sb::FitT*)pl->fit.p);
                         SB_OK(check_launch(pl, "k_tmpl_sums"));
                     }
-                    bool err_masks = false;
-                    for (int i = pb; i < pb + cnt; ++i) err_masks |= tm[i].errmode != 0;
-                    const bool fast = std::is_same<R, float>::value && pl->fast;
-                    const bool fast_fit = fast && !so.raw_amp && !err_masks && cnt <= sb::kFitMaxBatch;
-                    if constexpr (std::is_same<R, float>::value) {
+                    const bool fast_fit = fast && !so.raw_amp;
+                    if constexpr (kF32) {
                         if (fast) {
                             SB_OK(dispatch_n(Py, [&](auto nn) {
                                 constexpr int N = decltype(nn)::value;
@@ -565,72 +763,62 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                 return check_launch(pl, "k_conv_cols_f");
                             }));
                         }
-                        if (fast_fit) {
-                            SB_OK(dispatch_n(Px, [&](auto nn) {
-                                constexpr int N = decltype(nn)::value;
-                                using S = Shape<N, float>;
-                                ProfScope prof(pl, K_FIT_ROWS);
-                                if (pl->fit_threads == 0) {
+                    }
+                    if (!fast) {
+                        SB_OK(dispatch_n(Py, [&](auto nn) {
+                            constexpr int N = decltype(nn)::value;
+                            using S = Shape<N, R>;
+                            auto kern = sb::k_conv_cols<N, R>;
+                            SB_ALLOW_SMEM(kern, S::smem_conv);
+                            ProfScope prof(pl, K_CONV_COLS);
+                            SB_LAUNCH(kern, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem_conv,
+                                      pl->stream, g, d_tm, pb, a0, (const C4*)pl->trt.p, (const C2*)pl->fct.p,
+                                      (C4*)pl->gbuf.p, twy);
+                            return check_launch(pl, "k_conv_cols");
+                        }));
+                    }
+                    // fold: one launch per best state present in the chunk
+                    for (auto& gp : ch.groups) {
+                        const int* d_slots = gp.off < 0 ? nullptr : (const int*)pl->slots.p + gp.off;
+                        float* bsnr = pl->d_bsnr + (long)gp.state * bn - boff;
+                        float* bamp = pl->d_bamp + (long)gp.state * bn - boff;
+                        int* bidx = pl->d_bidx + (long)gp.state * bn - boff;
+                        if constexpr (kF32) {
+                            if (fast_fit) {
+                                SB_OK(dispatch_n(Px, [&](auto nn) {
+                                    constexpr int N = decltype(nn)::value;
+                                    using S = Shape<N, float>;
+                                    ProfScope prof(pl, K_FIT_ROWS);
                                     auto kern = sb::k_fit_rows_g<N>;
                                     SB_ALLOW_SMEM(kern, S::smem_fit_f);
                                     SB_LAUNCH(kern, dim3(div_up(Py / 2, S::GP)), dim3(S::threads), S::smem_fit_f,
-                                              pl->stream, g, cnt, (const sb::FitT*)pl->fit.p,
-                                              (const float4*)pl->gbuf.p, pl->d_bsnr, pl->d_bamp, pl->d_bidx,
-                                              (const float2*)twx);
+                                              pl->stream, g, gp.count, d_slots, (const sb::FitT*)pl->fit.p,
+                                              (const float4*)pl->gbuf.p, bsnr, bamp, bidx, (const float2*)twx,
+                                              gp.err ? (const int4*)pl->cross.p : (const int4*)nullptr);
                                     return check_launch(pl, "k_fit_rows_g");
+                                }));
+                                if (g.poison) {
+                                    SB_LAUNCH(sb::k_poison_windows, dim3(div_up((long)g.out_ny * g.out_nx, 256)), dim3(256), 0,
+                                              pl->stream, g, gp.count, d_slots, (const sb::FitT*)pl->fit.p, bsnr);
+                                    SB_OK(check_launch(pl, "k_poison_windows"));
                                 }
-                                if (S::T <= 256 && pl->fit_threads == 512) {
-                                    constexpr int threads = S::T > 512 ? S::T : 512;
-                                    constexpr int GP = threads / S::T;
-                                    constexpr size_t smem = S::smem_fit_f - S::smem_conv_f +
-                                                            (size_t)GP * 2 * sbfft::padded_len(N) * sizeof(float2);
-                                    auto kern = sb::k_fit_rows_f<N, 512>;
-                                    SB_ALLOW_SMEM(kern, smem);
-                                    SB_LAUNCH(kern, dim3(div_up(g.out_ny, GP)), dim3(threads), smem, pl->stream, g, cnt,
-                                              (const sb::FitT*)pl->fit.p, (const float4*)pl->gbuf.p, pl->d_bsnr,
-                                              pl->d_bamp, pl->d_bidx, (const float2*)twx);
-                                } else {
-                                    auto kern = sb::k_fit_rows_f<N, 256>;
-                                    SB_ALLOW_SMEM(kern, S::smem_fit_f);
-                                    SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem_fit_f,
-                                              pl->stream, g, cnt, (const sb::FitT*)pl->fit.p,
-                                              (const float4*)pl->gbuf.p, pl->d_bsnr, pl->d_bamp, pl->d_bidx,
-                                              (const float2*)twx);
-                                }
-                                return check_launch(pl, "k_fit_rows_f");
-                            }));
-                            if (g.poison) {
-                                SB_LAUNCH(sb::k_poison_windows, dim3(div_up((long)g.out_ny * g.out_nx, 256)), dim3(256), 0,
-                                          pl->stream, g, cnt, (const sb::FitT*)pl->fit.p, pl->d_bsnr);
-                                SB_OK(check_launch(pl, "k_poison_windows"));
+                                continue;
                             }
                         }
-                    }
-                    if (!fast) {
-                    SB_OK(dispatch_n(Py, [&](auto nn) {
-                        constexpr int N = decltype(nn)::value;
-                        using S = Shape<N, R>;
-                        auto kern = sb::k_conv_cols<N, R>;
-                        SB_ALLOW_SMEM(kern, S::smem_conv);
-                        ProfScope prof(pl, K_CONV_COLS);
-                        SB_LAUNCH(kern, dim3(div_up(KX, S::GP), cnt), dim3(S::threads), S::smem_conv,
-                                  pl->stream, g, d_tm, pb, a0, (const C4*)pl->trt.p, (const C2*)pl->fct.p,
-                                  (C4*)pl->gbuf.p, twy);
-                        return check_launch(pl, "k_conv_cols");
-                    }));
-                    }
-                    if (!fast_fit) {
-                    SB_OK(dispatch_n(Px, [&](auto nn) {
-                        constexpr int N = decltype(nn)::value;
-                        using S = Shape<N, R>;
-                        auto kern = sb::k_fit_rows<N, R>;
-                        SB_ALLOW_SMEM(kern, S::smem);
-                        ProfScope prof(pl, K_FIT_ROWS);
-                        SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
-                                  pl->stream, g, d_tm, pb, cnt, (const sb::TSum*)pl->sums.p,
-                                  (const C4*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
-                        return check_launch(pl, "k_fit_rows");
-                    }));
+                        sb::FitOut fo;
+                        fo.best_snr = bsnr; fo.best_amp = bamp; fo.best_idx = bidx;
+                        fo.raw_amp = so.raw_amp; fo.raw_snr = so.raw_snr;
+                        SB_OK(dispatch_n(Px, [&](auto nn) {
+                            constexpr int N = decltype(nn)::value;
+                            using S = Shape<N, R>;
+                            auto kern = sb::k_fit_rows<N, R>;
+                            SB_ALLOW_SMEM(kern, S::smem);
+                            ProfScope prof(pl, K_FIT_ROWS);
+                            SB_LAUNCH(kern, dim3(div_up(g.out_ny, S::GP)), dim3(S::threads), S::smem,
+                                      pl->stream, g, d_tm, pb, gp.count, d_slots, (const sb::TSum*)pl->sums.p,
+                                      (const C4*)pl->gbuf.p, (const double*)pl->d_x, (const double*)pl->d_y, fo, twx);
+                            return check_launch(pl, "k_fit_rows");
+                        }));
                     }
                 }
             }
@@ -674,6 +862,7 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
     if (!plan || ny < 1 || nx < 1) return fail("sb_plan_create: bad arguments");
     sb_plan* pl = new sb_plan();
     pl->ny = ny; pl->nx = nx; pl->dx = dx; pl->dx2 = dx2; pl->dy2 = dy2;
+    pl->slab_lo = 0; pl->slab_hi = ny; pl->row0 = 0; pl->drows = ny;
 #ifndef SB_EMU
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -693,17 +882,16 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
         }
         pl->own_stream = true;
     }
+    if (const char* e = std::getenv("SB_CONV_P")) pl->conv_persist = std::atoi(e);
+#ifdef SB_ABLATE
+    if (const char* e = std::getenv("SB_DBG")) pl->dbg = std::atoi(e);
+#endif
 #else
     (void)device; (void)stream;
 #endif
-    const size_t n = (size_t)ny * nx;
-    int e = 0;
-    e |= sb_rt_malloc((void**)&pl->d_bsnr, n * sizeof(float));
-    e |= sb_rt_malloc((void**)&pl->d_bamp, n * sizeof(float));
-    e |= sb_rt_malloc((void**)&pl->d_bidx, n * sizeof(int));
-    if (e) { sb_plan_destroy(pl); return fail("sb_plan_create: out of device memory"); }
+    if (alloc_best(pl) != 0) { sb_plan_destroy(pl); return fail("sb_plan_create: out of device memory"); }
     *plan = pl;
-    return sb_best_reset(pl);
+    return 0;
 }
 
 int sb_plan_destroy(sb_plan* pl) {
@@ -723,7 +911,7 @@ int sb_plan_destroy(sb_plan* pl) {
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
     for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
     for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                   &pl->tables, &pl->raw, &pl->tbox})
+                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux})
         release(*b);
 #ifndef SB_EMU
     if (pl->own_stream) cudaStreamDestroy(pl->stream);
@@ -743,17 +931,78 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
         return 0;
     }
     if (k == "force_pad") { pl->force_pad = value != 0; return 0; }
+    if (k == "mixed_tiles") { pl->mixed_tiles = value != 0; return 0; }
     if (k == "profile") { pl->profile = value != 0; return 0; }
     if (k == "fast") { pl->fast = value != 0; return 0; }
+    if (k == "conv_persist") { pl->conv_persist = (int)value; return 0; }
     if (k == "precision") {
         if (value != 32 && value != 64) return fail("precision must be 32 or 64");
         pl->precision = (int)value;
         return 0;
     }
+    if (k == "states") {
+        if (value < 1 || value > 64) return fail("states must be in [1, 64]");
+        if ((int)value != pl->n_states) {
+            pl->n_states = (int)value;
+            return alloc_best(pl);
+        }
+        return 0;
+    }
     return fail("unknown option " + k);
 }
 
+int sb_plan_set_slab(sb_plan* pl, int row_lo, int row_hi, int halo) {
+    if (!pl) return fail("null plan");
+    if (row_lo < 0 || row_hi > pl->ny || row_lo >= row_hi || halo < 0) return fail("sb_plan_set_slab: bad rows");
+    if (pl->d_dem && pl->own_dem) { sb_rt_free(pl->d_dem); }
+    pl->d_dem = nullptr; pl->own_dem = false;
+    if (pl->d_diffs) { sb_rt_free(pl->d_diffs); pl->d_diffs = nullptr; }
+    if (pl->d_diffs32) { sb_rt_free(pl->d_diffs32); pl->d_diffs32 = nullptr; }
+    pl->diffs64_valid = false;
+    pl->slab_lo = row_lo; pl->slab_hi = row_hi;
+    const long rows = (long)(row_hi - row_lo) + 2L * halo;
+    if (rows >= pl->ny) { pl->row0 = 0; pl->drows = pl->ny; }
+    else { pl->row0 = ((row_lo - halo) % pl->ny + pl->ny) % pl->ny; pl->drows = (int)rows; }
+    return alloc_best(pl);
+}
+
+int sb_plan_dem_rows(const sb_plan* pl, int* row0, int* drows) {
+    if (!pl) return fail("null plan");
+    if (row0) *row0 = pl->row0;
+    if (drows) *drows = pl->drows;
+    return 0;
+}
+
+int sb_plan_curv_stats(const sb_plan* pl, double* sumsq, double* count) {
+    if (!pl) return fail("null plan");
+    if (sumsq) *sumsq = pl->curv_sumsq;
+    if (count) *count = pl->curv_count;
+    return 0;
+}
+
+int sb_plan_set_curv_stats(sb_plan* pl, double sumsq, double count) {
+    if (!pl) return fail("null plan");
+    apply_curv_stats(pl, sumsq, count);
+    return 0;
+}
+
+void* sb_plan_stream(const sb_plan* pl) { return pl ? (void*)pl->stream : nullptr; }
+
 long sb_plan_launch_count(const sb_plan* pl) { return pl ? pl->launches : 0; }
+
+long sb_plan_device_bytes(const sb_plan* pl) {
+    if (!pl) return 0;
+    size_t b = 0;
+    const size_t n = (size_t)pl->drows * pl->nx;
+    if (pl->d_dem && pl->own_dem) b += n * sizeof(double);
+    if (pl->d_diffs) b += n * 3 * sizeof(double);
+    if (pl->d_diffs32) b += n * sizeof(float4);
+    b += (size_t)pl->bn() * pl->n_states * 12;
+    for (const Buf* q : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
+                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux})
+        b += q->cap;
+    return (long)b;
+}
 
 int sb_plan_profile(sb_plan* pl, double* ms6, long* launches6, int reset) {
     if (!pl) return fail("null plan");
@@ -772,9 +1021,11 @@ int sb_plan_last_geometry(const sb_plan* pl, int* out6) {
     return 0;
 }
 
+double sb_plan_last_fft_area(const sb_plan* pl) { return pl ? pl->last_fft_area : 0.0; }
+
 int sb_set_dem_host(sb_plan* pl, const double* dem_host) {
     if (!pl || !dem_host) return fail("sb_set_dem_host: null");
-    const size_t bytes = (size_t)pl->ny * pl->nx * sizeof(double);
+    const size_t bytes = (size_t)pl->drows * pl->nx * sizeof(double);
     if (!pl->own_dem || !pl->d_dem) {
         pl->d_dem = nullptr;
         SB_TRY(sb_rt_malloc((void**)&pl->d_dem, bytes));
@@ -782,7 +1033,7 @@ int sb_set_dem_host(sb_plan* pl, const double* dem_host) {
     }
     SB_TRY(sb_rt_h2d(pl->d_dem, dem_host, bytes, pl->stream));
     SB_TRY(sb_rt_sync(pl->stream));
-    return update_curv_scale(pl);
+    return after_dem(pl);
 }
 
 int sb_set_dem_dev(sb_plan* pl, const double* dem_dev) {
@@ -790,7 +1041,7 @@ int sb_set_dem_dev(sb_plan* pl, const double* dem_dev) {
     if (pl->own_dem && pl->d_dem) sb_rt_free(pl->d_dem);
     pl->own_dem = false;
     pl->d_dem = const_cast<double*>(dem_dev);
-    return update_curv_scale(pl);
+    return after_dem(pl);
 }
 
 int sb_set_axes_host(sb_plan* pl, const double* x_host, const double* y_host) {
@@ -806,6 +1057,7 @@ int sb_set_axes_host(sb_plan* pl, const double* x_host, const double* y_host) {
 int sb_directional_laplacian(sb_plan* pl, const sb_angle* angle, double* out, int out_is_device) {
     if (!pl || !angle || !out) return fail("sb_directional_laplacian: null");
     if (!pl->d_dem) return fail("no DEM set");
+    if (!pl->whole()) return fail("sb_directional_laplacian needs a plan over the whole raster");
     const long n = (long)pl->ny * pl->nx;
     double* dst = out;
     if (!out_is_device) {
@@ -856,6 +1108,7 @@ int sb_match_template(sb_plan* pl, const sb_angle* angle, const sb_template* tmp
     }
     sb_template t = *tmpl;
     t.angle_id = 0;
+    t.state = 0;
     SB_OK(run_sweep(pl, angle, 1, &t, 1, so));
     if (!out_is_device) {
         SB_TRY(sb_rt_d2h(amp, so.raw_amp, n * sizeof(double), pl->stream));
@@ -886,7 +1139,7 @@ int sb_match_template_raster(sb_plan* pl, const sb_angle* angle, const double* b
 
 int sb_best_reset(sb_plan* pl) {
     if (!pl) return fail("null plan");
-    const long n = (long)pl->ny * pl->nx;
+    const long n = pl->bn() * pl->n_states;
     SB_LAUNCH(sb::k_best_init, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, pl->d_bsnr, pl->d_bamp,
               pl->d_bidx);
     return check_launch(pl, "k_best_init");
@@ -897,10 +1150,13 @@ int sb_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_templat
     return run_sweep(pl, angles, n_angles, tmpls, n_tmpls, SweepOut());
 }
 
-int sb_finalize(sb_plan* pl, const double* age_of_host, const double* angle_of_host, int n_idx, double* out4,
-                int out_is_device) {
+int sb_finalize_ex(sb_plan* pl, int state, int row_lo, int row_hi, const double* age_of_host,
+                   const double* angle_of_host, int n_idx, double* out4, int out_is_device) {
     if (!pl || !age_of_host || !angle_of_host || !out4 || n_idx <= 0) return fail("sb_finalize: bad arguments");
-    const long n = (long)pl->ny * pl->nx;
+    if (state < 0 || state >= pl->n_states) return fail("sb_finalize: state out of range");
+    if (row_lo < pl->slab_lo || row_hi > pl->slab_hi || row_lo >= row_hi) return fail("sb_finalize: rows outside the plan");
+    const long n = (long)(row_hi - row_lo) * pl->nx;
+    const long off = (long)state * pl->bn() + (long)(row_lo - pl->slab_lo) * pl->nx;
     SB_OK(ensure(pl->tables, (size_t)2 * n_idx * sizeof(double)));
     double* d_age = (double*)pl->tables.p;
     double* d_ang = d_age + n_idx;
@@ -911,25 +1167,50 @@ int sb_finalize(sb_plan* pl, const double* age_of_host, const double* angle_of_h
         SB_OK(ensure(pl->raw, (size_t)n * 4 * sizeof(double)));
         dst = (double*)pl->raw.p;
     }
-    SB_LAUNCH(sb::k_finalize, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr,
-              (const float*)pl->d_bamp, (const int*)pl->d_bidx, (const double*)d_age, (const double*)d_ang, dst);
+    SB_LAUNCH(sb::k_finalize, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr + off,
+              (const float*)pl->d_bamp + off, (const int*)pl->d_bidx + off, (const double*)d_age, (const double*)d_ang,
+              n_idx, dst);
     SB_OK(check_launch(pl, "k_finalize"));
     if (!out_is_device) return copy_out(pl, out4, dst, (size_t)n * 4, 0);
     SB_TRY(sb_rt_sync(pl->stream));
     return 0;
 }
 
-int sb_best_state(sb_plan* pl, float** snr_dev, float** amp_dev, int32_t** idx_dev) {
+int sb_finalize(sb_plan* pl, const double* age_of_host, const double* angle_of_host, int n_idx, double* out4,
+                int out_is_device) {
     if (!pl) return fail("null plan");
-    if (snr_dev) *snr_dev = pl->d_bsnr;
-    if (amp_dev) *amp_dev = pl->d_bamp;
-    if (idx_dev) *idx_dev = pl->d_bidx;
+    return sb_finalize_ex(pl, 0, pl->slab_lo, pl->slab_hi, age_of_host, angle_of_host, n_idx, out4, out_is_device);
+}
+
+int sb_best_state_ex(sb_plan* pl, int state, float** snr_dev, float** amp_dev, int32_t** idx_dev) {
+    if (!pl) return fail("null plan");
+    if (state < 0 || state >= pl->n_states) return fail("state out of range");
+    const long off = (long)state * pl->bn();
+    if (snr_dev) *snr_dev = pl->d_bsnr + off;
+    if (amp_dev) *amp_dev = pl->d_bamp + off;
+    if (idx_dev) *idx_dev = pl->d_bidx + off;
     return 0;
+}
+
+int sb_best_state(sb_plan* pl, float** snr_dev, float** amp_dev, int32_t** idx_dev) {
+    return sb_best_state_ex(pl, 0, snr_dev, amp_dev, idx_dev);
+}
+
+int sb_best_merge(sb_plan* pl, int state, int row_lo, int row_hi, int n_cands, const float* snr_c, const float* amp_c,
+                  const int32_t* idx_c) {
+    if (!pl || !snr_c || !amp_c || !idx_c || n_cands < 1) return fail("sb_best_merge: bad arguments");
+    if (state < 0 || state >= pl->n_states) return fail("sb_best_merge: state out of range");
+    if (row_lo < pl->slab_lo || row_hi > pl->slab_hi || row_lo >= row_hi) return fail("sb_best_merge: rows outside the plan");
+    const long n = (long)(row_hi - row_lo) * pl->nx;
+    const long off = (long)state * pl->bn() + (long)(row_lo - pl->slab_lo) * pl->nx;
+    SB_LAUNCH(sb::k_best_merge, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, n_cands, snr_c, amp_c, (const int*)idx_c,
+              pl->d_bsnr + off, pl->d_bamp + off, pl->d_bidx + off);
+    return check_launch(pl, "k_best_merge");
 }
 
 int sb_best_pack(sb_plan* pl, unsigned long long* keys_dev) {
     if (!pl || !keys_dev) return fail("sb_best_pack: null");
-    const long n = (long)pl->ny * pl->nx;
+    const long n = pl->bn();
     SB_LAUNCH(sb::k_best_pack, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr,
               (const int*)pl->d_bidx, keys_dev);
     return check_launch(pl, "k_best_pack");
@@ -937,7 +1218,7 @@ int sb_best_pack(sb_plan* pl, unsigned long long* keys_dev) {
 
 int sb_best_select(sb_plan* pl, const unsigned long long* gkeys_dev, float* amp_out_dev) {
     if (!pl || !gkeys_dev || !amp_out_dev) return fail("sb_best_select: null");
-    const long n = (long)pl->ny * pl->nx;
+    const long n = pl->bn();
     SB_LAUNCH(sb::k_best_select, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, (const float*)pl->d_bsnr,
               (const float*)pl->d_bamp, (const int*)pl->d_bidx, gkeys_dev, amp_out_dev);
     return check_launch(pl, "k_best_select");
@@ -945,7 +1226,7 @@ int sb_best_select(sb_plan* pl, const unsigned long long* gkeys_dev, float* amp_
 
 int sb_best_unpack(sb_plan* pl, const unsigned long long* gkeys_dev, const float* amp_dev) {
     if (!pl || !gkeys_dev || !amp_dev) return fail("sb_best_unpack: null");
-    const long n = (long)pl->ny * pl->nx;
+    const long n = pl->bn();
     SB_LAUNCH(sb::k_best_unpack, dim3(div_up(n, 256)), dim3(256), 0, pl->stream, n, gkeys_dev, amp_dev,
               pl->d_bsnr, pl->d_bamp, pl->d_bidx);
     return check_launch(pl, "k_best_unpack");
@@ -968,6 +1249,72 @@ int sb_compare_host(sb_plan* pl, double* best4_host, const double* amp, const do
               (const double*)(d + 4 * n), d_age, d_ang, (const double*)(d + 5 * n), age_s, angle_s);
     SB_OK(check_launch(pl, "k_compare"));
     return copy_out(pl, best4_host, d, (size_t)n * 4, 0);
+}
+
+int sb_curvature_noise_moments(sb_plan* pl, double sigma, double truncate, double* out10_host) {
+    if (!pl || !out10_host || !(sigma > 0.0) || !(truncate > 0.0)) return fail("sb_curvature_noise_moments: bad arguments");
+    if (!pl->d_dem) return fail("no DEM set");
+    if (!pl->whole()) return fail("sb_curvature_noise_moments needs a plan over the whole raster");
+    const int ny = pl->ny, nx = pl->nx;
+    const long n = (long)ny * nx;
+    const int radius = (int)(truncate * sigma + 0.5);          // scipy.ndimage.gaussian_filter1d
+    std::vector<double> w(2 * radius + 1);
+    {
+        double s = 0.0;
+        for (int k = -radius; k <= radius; ++k) { w[k + radius] = std::exp(-0.5 / (sigma * sigma) * (double)k * (double)k); s += w[k + radius]; }
+        for (auto& v : w) v /= s;
+    }
+    SB_OK(ensure_diffs64(pl));
+    // aux: weights | 4 planes in (dxx, dxy, dyy, nan flag) column-filtered | 4 planes fully filtered | partial sums
+    const int blocks = std::max(1, std::min(2048, div_up(n, 256)));
+    const size_t wbytes = (w.size() * sizeof(double) + 255) / 256 * 256;
+    SB_OK(ensure(pl->aux, wbytes + (size_t)n * 8 * sizeof(double) + (size_t)blocks * 10 * sizeof(double)));
+    double* d_w = (double*)pl->aux.p;
+    double* d_tmp = (double*)((char*)pl->aux.p + wbytes);
+    double* d_low = d_tmp + 4 * n;
+    double* d_part = d_low + 4 * n;
+    SB_TRY(sb_rt_h2d(d_w, w.data(), w.size() * sizeof(double), pl->stream));
+    SB_LAUNCH(sb::k_gauss_axis0, dim3(div_up(n, 256), 4), dim3(256), 0, pl->stream, ny, nx, radius, (const double*)d_w,
+              (const double*)pl->d_diffs, (const double*)pl->d_dem, d_tmp);
+    SB_OK(check_launch(pl, "k_gauss_axis0"));
+    SB_LAUNCH(sb::k_gauss_axis1, dim3(div_up(n, 256), 4), dim3(256), 0, pl->stream, ny, nx, radius, (const double*)d_w,
+              (const double*)d_tmp, d_low);
+    SB_OK(check_launch(pl, "k_gauss_axis1"));
+    SB_LAUNCH(sb::k_noise_moments, dim3(blocks), dim3(256), 256 * 10 * sizeof(double), pl->stream, n,
+              (const double*)pl->d_diffs, (const double*)pl->d_dem, (const double*)d_low, d_part);
+    SB_OK(check_launch(pl, "k_noise_moments"));
+    std::vector<double> part((size_t)blocks * 10);
+    SB_TRY(sb_rt_d2h(part.data(), d_part, part.size() * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    for (int k = 0; k < 10; ++k) {
+        double s = 0.0;
+        for (int b = 0; b < blocks; ++b) s += part[(size_t)b * 10 + k];
+        out10_host[k] = s;
+    }
+    return 0;
+}
+
+int sb_fill_nodata(sb_plan* pl, double* dem_host_inout, double max_search_distance, long* remaining) {
+    if (!pl || !dem_host_inout) return fail("sb_fill_nodata: null");
+    if (!pl->whole()) return fail("sb_fill_nodata needs a plan over the whole raster");
+    const long n = (long)pl->ny * pl->nx;
+    SB_OK(ensure(pl->aux, (size_t)n * 2 * sizeof(double) + 1024 * sizeof(long)));
+    double* d_in = (double*)pl->aux.p;
+    double* d_out = d_in + n;
+    long* d_cnt = (long*)(d_out + n);
+    SB_TRY(sb_rt_h2d(d_in, dem_host_inout, (size_t)n * sizeof(double), pl->stream));
+    SB_TRY(sb_rt_memset(d_cnt, 0, sizeof(long) * 1024, pl->stream));
+    const int blocks = div_up(n, 256);
+    SB_LAUNCH(sb::k_fill_nodata, dim3(blocks), dim3(256), 0, pl->stream, pl->ny, pl->nx, (const double*)d_in, d_out,
+              max_search_distance, d_cnt);
+    SB_OK(check_launch(pl, "k_fill_nodata"));
+    std::vector<long> cnt(1024);
+    SB_TRY(sb_rt_d2h(cnt.data(), d_cnt, sizeof(long) * 1024, pl->stream));
+    SB_OK(copy_out(pl, dem_host_inout, d_out, (size_t)n, 0));
+    long left = 0;
+    for (long v : cnt) left += v;
+    if (remaining) *remaining = left;
+    return 0;
 }
 
 int sb_debug_fft(sb_plan* pl, int n, int rows, const float* in_host, float* out_host, int inverse) {

@@ -1,7 +1,14 @@
 """In-memory DEM container as the hot path consumes it (dem.py:203-218, 351-372 of the
-reference): ``_griddata`` (float64, ny x nx) and ``_georef_info.dx / .dy``.  File I/O
+reference): ``_griddata`` (float64, ny x nx) and ``_georef_info.dx / .dy``.  Reading rasters
 (GDAL / rasterio) is outside the scope of this package; any object with those two
-attributes — including the reference's own ``DEMGrid`` — is accepted by ``core``."""
+attributes — including the reference's own ``DEMGrid`` — is accepted by ``core``.  The
+methods either side of the match path are here, on the GPU where they compute:
+
+* ``_calculate_directional_laplacian``       dem.py:68-107
+* ``_estimate_curvature_noiselevel``         dem.py:152-179
+* ``_fill_nodata``                           dem.py:388-414 (device fill in place of rasterio)
+* ``save``                                   dem.py:291-306 (dependency-free GeoTIFF writer)
+"""
 import numpy as np
 
 
@@ -27,17 +34,78 @@ class DEMGrid(object):
         ny, nx = self._griddata.shape
         self._georef_info = GeorefInfo(dx, dy, nx, ny)
         self.shape = self._griddata.shape
+        self.nodata_value = np.nan
         self.is_interpolated = False
+
+    def _plan(self):
+        from .engine import Plan
+        ny, nx = self._griddata.shape
+        return Plan(ny, nx, self._georef_info.dx, self._georef_info.dy)
 
     def _calculate_directional_laplacian(self, alpha):
         """dem.py:68-107, evaluated by the CUDA stencil in float64 (bit-exact with the
         NumPy reference).  Unlike the reference the input grid is not modified."""
-        from .engine import Plan
-        ny, nx = self._griddata.shape
-        with Plan(ny, nx, self._georef_info.dx, self._georef_info.dy) as plan:
+        with self._plan() as plan:
             plan.set_dem(self._griddata)
             return plan.directional_laplacian(alpha)
 
     def _calculate_laplacian(self):
         """dem.py:62-66"""
         return self._calculate_directional_laplacian(0)
+
+    def _estimate_curvature_noiselevel(self, sigma=100, truncate=4.0):
+        """Mean and standard deviation of the high-passed directional curvature for 180
+        directions (dem.py:152-179): ``highpass = del2z - gaussian_filter(del2z, 100)``,
+        ``nanmean`` / ``nanstd`` per direction.  Returns ``(angles, mean, sd)`` like the
+        reference (``mean`` and ``sd`` are lists of 180 floats).
+
+        The directional Laplacian is linear in the second differences (dem.py:103-104) and so
+        is the Gaussian filter: the device filters dxx, dxy, dyy once and reduces them to ten
+        moments; the 180 directions are quadratic forms of those (instead of 180 Laplacians
+        and 180 filters)."""
+        angles = np.linspace(0, np.pi, num=180)                      # dem.py:166
+        with self._plan() as plan:
+            plan.set_dem(self._griddata)
+            m = plan.curvature_noise_moments(sigma, truncate)
+        cnt = m[0]
+        if cnt <= 0:
+            nan = [float("nan")] * len(angles)
+            return angles, list(nan), list(nan)
+        s_xx, s_xy, s_yy, q_xx, q_xy, q_yy, q_xx_xy, q_xx_yy, q_xy_yy = m[1:] / cnt
+        c2, s2 = np.cos(angles) ** 2, np.sin(angles) ** 2            # dem.py:103-104
+        sc = 2 * np.sin(angles) * np.cos(angles)
+        mean = s_xx * c2 - s_xy * sc + s_yy * s2
+        second = (q_xx * c2 ** 2 + q_xy * sc ** 2 + q_yy * s2 ** 2
+                  - 2 * q_xx_xy * c2 * sc + 2 * q_xx_yy * c2 * s2 - 2 * q_xy_yy * sc * s2)
+        sd = np.sqrt(np.maximum(second - mean ** 2, 0.0))
+        return angles, [float(v) for v in mean], [float(v) for v in sd]
+
+    def _fill_nodata(self):
+        """Fill nodata cells by interpolation, in place (dem.py:388-414).  The reference
+        wraps ``rasterio.fill.fillnodata`` (GDAL's inverse-distance fill); here each pass is
+        a CUDA kernel: a nodata cell becomes the inverse-distance-weighted mean of the
+        nearest valid cell along the eight row / column / diagonal rays, with the
+        reference's search distance (half the longest nodata run count, dem.py:403-405) and
+        its loop until nothing is left (dem.py:402)."""
+        if ~np.isnan(self.nodata_value):                             # dem.py:392-395
+            self._griddata[self._griddata == self.nodata_value] = np.nan
+        self.nodata_mask = np.isnan(self._griddata)
+        num = int(self.nodata_mask.sum())
+        if num and num < self._griddata.size:
+            z = np.ascontiguousarray(self._griddata, dtype=np.float64)
+            with self._plan() as plan:
+                prev = None
+                while num > 0 and num != prev:                       # dem.py:402
+                    mask = np.isnan(z)
+                    col_nodata = mask.sum(axis=0).max()              # dem.py:403-405
+                    row_nodata = mask.sum(axis=1).max()
+                    dist = max(row_nodata, col_nodata) / 2
+                    prev = num
+                    num = plan.fill_nodata_pass(z, max(dist, 1.0))
+            self._griddata = z
+        self.is_interpolated = True
+
+    def save(self, filename, epsg=None):
+        """Save the grid as a single-band Float32 GeoTIFF (dem.py:291-306)."""
+        from .geotiff import write_geotiff, _transform_of
+        return write_geotiff(filename, self._griddata, geo_transform=_transform_of(self._georef_info), epsg=epsg)

@@ -3,8 +3,9 @@ workspace for one raster shape and drives sweeps.  Thin by design — tiling, ba
 and every kernel launch live in the CUDA library."""
 import ctypes
 import os
-import sys
-from ctypes import byref, c_int, c_void_p
+import threading
+import weakref
+from ctypes import byref, c_double, c_int, c_long, c_void_p
 
 import numpy as np
 
@@ -43,10 +44,17 @@ class Plan(object):
     """One raster geometry bound to one CUDA device."""
 
     def __init__(self, ny, nx, dx, dy, device=-1, stream=None, workspace_mb=None,
-                 max_fft=None, force_pad=None, precision=None):
+                 max_fft=None, force_pad=None, precision=None, slab=None, states=1):
+        """``slab=(row_lo, row_hi, halo)``: the plan keeps the geometry of the whole ``ny x nx``
+        raster but computes (and holds the DEM for) that band of rows only -- one rank's share
+        of a raster sharded spatially over GPUs.  ``states``: independent best states (one per
+        template scale of a multi-scale search)."""
         self.lib = _lib.load()
         self.ny, self.nx = int(ny), int(nx)
         self.dx, self.dy = dx, dy
+        self.row_lo, self.row_hi = 0, self.ny
+        self.states = 1
+        self._pool_lock = threading.Lock()
         self._h = c_void_p()
         # dx ** 2 / dy ** 2 evaluated in Python like dem.py:95,99
         check(self.lib, self.lib.sb_plan_create(byref(self._h), self.ny, self.nx, float(dx),
@@ -66,6 +74,10 @@ class Plan(object):
             self.set_option("precision", precision)
         if force_pad is not None:
             self.set_option("force_pad", int(force_pad))
+        if states != 1:
+            self.set_states(states)
+        if slab is not None:
+            self.set_slab(*slab)
 
     # -- lifecycle ---------------------------------------------------------
     def close(self):
@@ -88,6 +100,46 @@ class Plan(object):
 
     def set_option(self, key, value):
         check(self.lib, self.lib.sb_plan_set_option(self._h, key.encode(), int(value)))
+
+    def set_states(self, n):
+        """Number of independent best states (resets them)."""
+        self.set_option("states", int(n))
+        self.states = int(n)
+
+    def set_slab(self, row_lo, row_hi, halo):
+        """Restrict the plan to raster rows ``row_lo .. row_hi - 1`` (see ``__init__``)."""
+        check(self.lib, self.lib.sb_plan_set_slab(self._h, int(row_lo), int(row_hi), int(halo)))
+        self.row_lo, self.row_hi = int(row_lo), int(row_hi)
+        self.__dict__.pop("_result_pool", None)
+
+    def dem_rows(self):
+        """(first raster row, number of rows) of the DEM band the plan holds (periodic in ny)."""
+        r0, n = c_int(), c_int()
+        check(self.lib, self.lib.sb_plan_dem_rows(self._h, byref(r0), byref(n)))
+        return r0.value, n.value
+
+    @property
+    def stream_handle(self):
+        """The ``cudaStream_t`` (as an integer) the plan's work is ordered on."""
+        return int(self.lib.sb_plan_stream(self._h) or 0)
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.sb_plan_device_bytes(self._h))
+
+    @property
+    def fft_area(self):
+        """Sum over the FFT tiles of the last sweep of Py * Px."""
+        return float(self.lib.sb_plan_last_fft_area(self._h))
+
+    def curv_stats(self):
+        s, n = c_double(), c_double()
+        check(self.lib, self.lib.sb_plan_curv_stats(self._h, byref(s), byref(n)))
+        return s.value, n.value
+
+    def set_curv_stats(self, sumsq, count):
+        """Totals over all slabs of a sharded raster (see ``distributed.share_dem_stats``)."""
+        check(self.lib, self.lib.sb_plan_set_curv_stats(self._h, float(sumsq), float(count)))
 
     @property
     def launches(self):
@@ -115,14 +167,20 @@ class Plan(object):
 
     # -- inputs --------------------------------------------------------------
     def set_dem(self, z):
-        """Upload ``DEMGrid._griddata`` (host float64, never modified)."""
+        """Upload ``DEMGrid._griddata`` (host float64, never modified).  A slab plan takes
+        either the whole raster (its band is cut out here) or just the band ``dem_rows()``
+        describes."""
+        r0, nrows = self.dem_rows()
+        if np.shape(z) == (self.ny, self.nx) and nrows != self.ny:
+            z = np.take(z, (r0 + np.arange(nrows)) % self.ny, axis=0)
         z = _as_f64(z)
-        if z.shape != (self.ny, self.nx):
-            raise ValueError("DEM shape %r does not match the plan %r" % (z.shape, (self.ny, self.nx)))
+        if z.shape != (nrows, self.nx):
+            raise ValueError("DEM shape %r does not match the plan %r" % (z.shape, (nrows, self.nx)))
         check(self.lib, self.lib.sb_set_dem_host(self._h, z.ctypes.data))
 
     def set_dem_device(self, ptr):
-        """Borrow a float64 device buffer (e.g. ``tensor.data_ptr()``)."""
+        """Borrow a float64 device buffer (e.g. ``tensor.data_ptr()``) holding the rows
+        ``dem_rows()`` describes; it must outlive the plan's use of it."""
         check(self.lib, self.lib.sb_set_dem_dev(self._h, c_void_p(int(ptr))))
 
     # -- single operations -----------------------------------------------------
@@ -182,10 +240,14 @@ class Plan(object):
         ``"angle_major"`` = ``calculate_best_fit_parameters_serial`` (core.py:116-134).
         ``angle_slice`` restricts the records to a contiguous shard of the angle list
         (multi-GPU) without changing any index.
+        ``scale`` may be a sequence: one best state per scale (``Plan(states=len(scale))``),
+        all scales of an orientation in the same sweep so that they share its curvature
+        spectra; every state uses the same flat index space.
         Returns ``(angle_records, template_records, age_of, angle_of)``.
         """
         ages = np.atleast_1d(np.asarray(ages, dtype=np.float64))
         angles = np.asarray(angles, dtype=np.float64)
+        scales = [scale] if np.ndim(scale) == 0 else list(scale)
         A, G = len(angles), len(ages)
         lo, hi = (0, A) if angle_slice is None else angle_slice
         ai, gi = np.meshgrid(np.arange(A), np.arange(G), indexing="ij")
@@ -197,10 +259,11 @@ class Plan(object):
         arr_a = (SbAngle * max(hi - lo, 1))()
         for k, a in enumerate(range(lo, hi)):
             arr_a[k] = P.angle_record(angles[a])
-        recs = P.template_records(spec, scale, ages, angles[lo:hi], self.nx, self.ny, self.dx,
-                                  self.x, self.y, np.arange(hi - lo), idx[lo:hi])
-        arr_t = P.records_to_ctypes(recs)
-        n = (hi - lo) * G
+        recs = [P.template_records(spec, sc, ages, angles[lo:hi], self.nx, self.ny, self.dx,
+                                   self.x, self.y, np.arange(hi - lo), idx[lo:hi], state=k)
+                for k, sc in enumerate(scales)]
+        arr_t = P.records_to_ctypes(np.stack(recs, axis=1))                 # [angle][scale][age]
+        n = (hi - lo) * G * len(scales)
         return (arr_a, hi - lo), (arr_t, n), age_of, angle_of
 
     def reset(self):
@@ -213,44 +276,79 @@ class Plan(object):
             return
         check(self.lib, self.lib.sb_sweep(self._h, arr_a, na, arr_t, nt))
 
-    def _result_array(self):
-        """Host array for a (4, ny, nx) result.  The first result of a plan is an ordinary
+    # -- results -----------------------------------------------------------------
+    def _result_array(self, rows):
+        """Host array for a (4, rows, nx) result.  The first result of a plan is an ordinary
         NumPy array.  A plan that keeps producing results (a service looping over rasters of
-        one shape) hands out page-locked arrays from a small pool instead: the 32 B/px
-        device-to-host copy then runs at PCIe speed instead of through page faults and the
-        driver's bounce buffers (5x).  A pooled array is only reused once the caller has
-        dropped every reference to it (and to views of it), so results never alias."""
-        shape = (4, self.ny, self.nx)
+        one shape, or the plan cache behind ``core.match``) hands out page-locked arrays from
+        a small pool instead: the 32 B/px device-to-host copy then runs at PCIe speed instead
+        of through page faults and the driver's bounce buffers (5x).  Ownership is explicit:
+        an entry is busy from the moment its array is handed out until that array object --
+        which every view of it keeps alive through ``.base`` -- is garbage collected
+        (``weakref.finalize``), so results never alias, whatever the interpreter does with
+        reference counts."""
+        shape = (4, rows, self.nx)
         self._n_results = getattr(self, "_n_results", 0) + 1
         if self._n_results < 2:
             return np.empty(shape, dtype=np.float64)
-        pool = self.__dict__.setdefault("_result_pool", [])
-        for _, arr in pool:
-            if sys.getrefcount(arr) <= 3:          # the pool's tuple, the loop variable, the argument
-                return arr
-        if len(pool) < 3:
-            try:
-                import torch
-                ten = torch.empty(shape, dtype=torch.float64, pin_memory=True)
-                arr = ten.numpy()
-                pool.append((ten, arr))
-                return arr
-            except Exception:                      # no torch / no page-locked memory left
-                pass
-        return np.empty(shape, dtype=np.float64)
+        with self._pool_lock:
+            pool = self.__dict__.setdefault("_result_pool", [])
+            entry = next((e for e in pool if not e["busy"] and e["rows"] == rows), None)
+            if entry is None and len(pool) < 3:
+                try:
+                    import torch
+                    entry = {"tensor": torch.empty(shape, dtype=torch.float64, pin_memory=True),
+                             "busy": False, "rows": rows}
+                    pool.append(entry)
+                except Exception:                  # no torch / no page-locked memory left
+                    entry = None
+            if entry is None:
+                return np.empty(shape, dtype=np.float64)
+            entry["busy"] = True
+        arr = entry["tensor"].numpy()              # a fresh ndarray object over the pinned block
 
-    def finalize(self, age_of, angle_of):
-        """(4, ny, nx) float64 stack [amp, age, angle, snr] (core.py:190-193)."""
+        def _release(e=entry, lock=self._pool_lock):
+            with lock:
+                e["busy"] = False
+        weakref.finalize(arr, _release)
+        return arr
+
+    def finalize(self, age_of, angle_of, state=0, rows=None, out=None):
+        """(4, rows, nx) float64 stack [amp, age, angle, snr] (core.py:190-193) of best state
+        ``state``; ``rows=(lo, hi)`` restricts it to a band of the plan's rows (default: all
+        of them).  ``out``: a caller-owned C-contiguous float64 array of that shape (e.g.
+        page-locked) to fill instead of a new one."""
         age_of, angle_of = _as_f64(age_of), _as_f64(angle_of)
-        out = self._result_array()
-        check(self.lib, self.lib.sb_finalize(self._h, age_of.ctypes.data, angle_of.ctypes.data,
-                                             len(age_of), out.ctypes.data, 0))
+        lo, hi = (self.row_lo, self.row_hi) if rows is None else (int(rows[0]), int(rows[1]))
+        if out is None:
+            out = self._result_array(hi - lo)
+        elif (out.shape != (4, hi - lo, self.nx) or out.dtype != np.float64 or
+              not out.flags["C_CONTIGUOUS"]):
+            raise ValueError("out must be a C-contiguous float64 array of shape %r" % ((4, hi - lo, self.nx),))
+        check(self.lib, self.lib.sb_finalize_ex(self._h, int(state), lo, hi, age_of.ctypes.data,
+                                                angle_of.ctypes.data, len(age_of), out.ctypes.data, 0))
         return out
 
-    def best_state_pointers(self):
+    def finalize_device(self, age_of, angle_of, out_ptr, state=0, rows=None):
+        """``finalize`` into device memory (4 * rows * nx float64 at ``out_ptr``)."""
+        age_of, angle_of = _as_f64(age_of), _as_f64(angle_of)
+        lo, hi = (self.row_lo, self.row_hi) if rows is None else (int(rows[0]), int(rows[1]))
+        check(self.lib, self.lib.sb_finalize_ex(self._h, int(state), lo, hi, age_of.ctypes.data,
+                                                angle_of.ctypes.data, len(age_of), c_void_p(int(out_ptr)), 1))
+
+    def best_state_pointers(self, state=0):
+        """Device pointers (snr float32, amp float32, idx int32) of best state ``state``:
+        one value per pixel of the plan's rows."""
         s, a, i = c_void_p(), c_void_p(), c_void_p()
-        check(self.lib, self.lib.sb_best_state(self._h, byref(s), byref(a), byref(i)))
+        check(self.lib, self.lib.sb_best_state_ex(self._h, int(state), byref(s), byref(a), byref(i)))
         return s.value, a.value, i.value
+
+    def best_merge(self, state, rows, n_cands, snr_ptr, amp_ptr, idx_ptr):
+        """Fold ``n_cands`` candidate states for raster rows ``rows`` (device buffers laid out
+        [candidate][row][nx]) into best state ``state``."""
+        check(self.lib, self.lib.sb_best_merge(self._h, int(state), int(rows[0]), int(rows[1]), int(n_cands),
+                                               c_void_p(int(snr_ptr)), c_void_p(int(amp_ptr)),
+                                               c_void_p(int(idx_ptr))))
 
     def best_pack(self, keys_ptr):
         check(self.lib, self.lib.sb_best_pack(self._h, c_void_p(int(keys_ptr))))
@@ -281,6 +379,21 @@ class Plan(object):
             angle_p.ctypes.data if angle_p is not None else None,
             snr.ctypes.data, age_s, angle_s))
         return best4
+
+    def curvature_noise_moments(self, sigma=100.0, truncate=4.0):
+        """Sums behind ``DEMGrid._estimate_curvature_noiselevel`` (dem.py:152-179), see
+        ``sb_curvature_noise_moments``."""
+        out = (c_double * 10)()
+        check(self.lib, self.lib.sb_curvature_noise_moments(self._h, float(sigma), float(truncate), out))
+        return np.array(list(out), dtype=np.float64)
+
+    def fill_nodata_pass(self, z, max_search_distance):
+        """One filling pass over a host raster (modified in place); returns the NaN count left."""
+        if z.shape != (self.ny, self.nx) or z.dtype != np.float64 or not z.flags["C_CONTIGUOUS"]:
+            raise ValueError("fill_nodata_pass needs the plan's C-contiguous float64 raster")
+        left = c_long()
+        check(self.lib, self.lib.sb_fill_nodata(self._h, z.ctypes.data, float(max_search_distance), byref(left)))
+        return int(left.value)
 
     def debug_fft(self, x, inverse=False):
         x = np.ascontiguousarray(x, dtype=np.complex64)

@@ -148,7 +148,7 @@ TEMPLATE_DTYPE = np.dtype([(name, np.float64 if ctype is SbTemplate._fields_[0][
                            for name, ctype in SbTemplate._fields_], align=True)
 
 
-def template_records(spec, scale, ages, angles, nx, ny, de, x, y, angle_ids, idx):
+def template_records(spec, scale, ages, angles, nx, ny, de, x, y, angle_ids, idx, state=0):
     """All ``SbTemplate`` records of the fan-out ``angles`` x ``ages`` at once: a structured
     array of shape (len(angles), len(ages)), field for field what ``template_record``
     returns (tests/test_host_logic.py holds the two against each other).  The reference
@@ -163,7 +163,7 @@ def template_records(spec, scale, ages, angles, nx, ny, de, x, y, angle_ids, idx
         for a in range(A):
             for g in range(G):
                 rec = template_record(spec, scale, ages[g], angles[a], nx, ny, de, x, y,
-                                      angle_ids[a], idx[a][g])
+                                      angle_ids[a], idx[a][g], state)
                 out[a, g] = tuple(getattr(rec, name) for name, _ in SbTemplate._fields_)
         return out
     alpha = [-float(a) for a in angles]              # WindowedTemplate.py:151, 489
@@ -205,6 +205,7 @@ def template_records(spec, scale, ages, angles, nx, ny, de, x, y, angle_ids, idx
         out["i_lo"], out["i_hi"], out["j_lo"], out["j_hi"] = 0, ny - 1, 0, nx - 1
     out["angle_id"] = np.asarray(angle_ids, dtype=np.int32)[:, None]
     out["idx"] = np.asarray(idx, dtype=np.int32)
+    out["state"] = int(state)
     return out
 
 
@@ -217,7 +218,7 @@ def records_to_ctypes(records):
     return arr
 
 
-def template_record(spec, scale, age, angle, nx, ny, de, x, y, angle_id, idx):
+def template_record(spec, scale, age, angle, nx, ny, de, x, y, angle_id, idx, state=0):
     """``SbTemplate`` for ``Template(scale, age, angle, nx, ny, de)`` (core.py:345)."""
     alpha = -angle                                   # WindowedTemplate.py:151, 489
     ca = float(np.cos(alpha))
@@ -247,4 +248,4 @@ def template_record(spec, scale, age, angle, nx, ny, de, x, y, angle_id, idx):
     tscale = packing_scale(spec.kind, k0, k1, c_eff)
     return SbTemplate(ca, sa, c, d, k0, k1, float(spec.sign), tscale, spec.kind, spec.errmode,
                       sy_lo, sy_hi, sx_lo, sx_hi, i_lo, i_hi, j_lo, j_hi,
-                      int(angle_id), int(idx))
+                      int(angle_id), int(idx), int(state), 0)

@@ -132,17 +132,36 @@ _BUILTIN_BY_NAME = {cls.__name__: cls for cls in
                     (Scarp, RightFacingUpperBreakScarp, LeftFacingUpperBreakScarp, Ricker, Channel)}
 
 
+# the plugin surface a subclass may override (core.py:345-346, 369-375)
+_SURFACE = ("__init__", "template", "template_numexpr", "get_coordinates", "get_mask",
+            "get_window_limits", "get_err_mask")
+
+
 def device_spec(Template):
-    """Device generator for a template class.  Accepts this package's classes and the
-    reference's own built-ins (matched by name when they come from
-    ``scarplet.WindowedTemplate``), so ``sl.match(data, scarplet.WindowedTemplate.Scarp)``
-    style call sites keep working.  ``None`` for any other class: it is served through its own
-    ``template()`` / ``get_window_limits()`` / ``get_err_mask()`` methods (core._plugin_*)."""
-    spec = getattr(Template, "_sb_spec", None)
-    if spec is not None:
-        return spec
+    """Device generator for a template class, or ``None``.
+
+    Only a class that IS one of the built-ins keeps the on-device generator: this package's
+    classes, the reference's own built-ins (matched by name when they come from
+    ``scarplet.WindowedTemplate``, so ``sl.match(data, scarplet.WindowedTemplate.Scarp)`` style
+    call sites keep working), and subclasses of this package's built-ins that leave the whole
+    plugin surface (constructor, ``template()``, masks, coordinates) untouched or declare their
+    own ``_sb_spec``.  A subclass that overrides any of it -- the reference's
+    ``ShiftedTemplateMixin`` pattern (WindowedTemplate.py:307-431) rebuilt on these classes, a
+    rescaled ``template()`` ... -- is a plugin class: ``None`` is returned and it is served
+    through its own methods (core._plugin_*), never silently replaced by its base."""
+    if not isinstance(Template, type):
+        return None
+    if Template in _BUILTIN_BY_NAME.values():
+        return Template._sb_spec
     mod = getattr(Template, "__module__", "")
     name = getattr(Template, "__name__", "")
     if mod.startswith("scarplet.") and name in _BUILTIN_BY_NAME:
         return _BUILTIN_BY_NAME[name]._sb_spec
+    for cls in Template.__mro__:
+        if cls in _BUILTIN_BY_NAME.values():
+            return cls._sb_spec               # nothing overridden on the way down to a built-in
+        if "_sb_spec" in cls.__dict__ and cls.__dict__["_sb_spec"] is not None:
+            return cls.__dict__["_sb_spec"]   # the subclass names its generator itself
+        if any(attr in cls.__dict__ for attr in _SURFACE):
+            return None
     return None        # a plugin class: core.py renders it on the host (generic path)

@@ -29,6 +29,7 @@ static inline float4 make_float4(float x, float y, float z, float w) {
 }
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct alignas(16) double4 { double x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
 static inline double4 make_double4(double x, double y, double z, double w) {
     double4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r;
 }

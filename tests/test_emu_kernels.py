@@ -163,7 +163,9 @@ def test_persistent_column_kernel(emu_lib, scale, ages):
                      for age in ages for ang in angles), ny, nx)
     rep = stack_report(outs["1"], np.stack(ref))
     assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.999, rep
-    assert rep["snr_rel_p50"] < 1e-5 and rep["frac_snr_over_tol"] <= 2e-2, rep
+    # a 200-column strip holds nothing a scale-70 scarp fits (median SNR 0.07): the bound applies
+    # to the upper half of the SNR range, the rest is noise-level
+    assert rep["snr_rel_p50"] < 1e-5 and rep["snr_rel_max_strong"] <= 1e-4, rep
 
 
 @pytest.mark.parametrize("shape,angle", [((128, 128), 0.3), ((90, 140), -0.8)])
@@ -212,21 +214,33 @@ def test_nan_in_dem_search(emu_lib):
     assert np.array_equal(res[1], ref[1]) and np.array_equal(res[2], ref[2])
 
 
-def test_match_scales_equals_per_scale_match(emu_lib):
-    """The multi-scale entry (one result per scale, DEM set-up shared) returns exactly what
-    match() returns for each scale on its own."""
+def test_match_scales_one_sweep(emu_lib):
+    """The multi-scale entry runs every scale in ONE device sweep (an orientation's curvature
+    spectra are shared, each scale folds into its own best state): each result equals the
+    oracle's for that scale and the per-scale match() (same masks and indices; values to
+    rounding, because the shared FFT domain is sized for the largest scale)."""
     import scarplet_b200 as sl
     from scarplet_b200.WindowedTemplate import Scarp
     from scarplet_b200.synth import synthetic_dem
-    z = synthetic_dem(96, seed=8, nx=128, relief=3.0)
+    z = synthetic_dem(96, seed=8, nx=128)
     grid = sl.DEMGrid(z, 1.0)
-    multi = sl.match_scales(grid, Scarp, [6, 10], age=3.0, ang_min=-0.2, ang_max=0.2)
-    for scale in (6, 10):
+    multi = sl.match_scales(grid, Scarp, [6, 10, 14], age=3.0, ang_min=-0.2, ang_max=0.2)
+    assert sorted(multi) == [6, 10, 14]
+    for scale in (6, 10, 14):
         single = sl.match(grid, Scarp, scale=scale, age=3.0, ang_min=-0.2, ang_max=0.2)
-        assert np.array_equal(multi[scale], single)
+        assert np.array_equal(multi[scale][3] > 0, single[3] > 0)
+        assert np.array_equal(multi[scale][1], single[1])
+        rep = stack_report(multi[scale], single)
+        assert rep["index_agreement"] >= 0.999 and rep["snr_rel_max_strong"] < 1e-5, rep
+        ref = O.calculate_best_fit_parameters(z, 1.0, 1.0, O.SCARP, scale, 3.0, ang_max=0.2, ang_min=-0.2,
+                                              processes=2)
+        rep = stack_report(multi[scale], ref)
+        assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.999, rep
+        assert rep["snr_rel_max_strong"] <= 1e-4 and rep["amp_rel_max_strong"] <= 1e-4, rep
     sweep = sl.match_scales(grid, Scarp, [8], ages=[2.0, 9.0], ang_min=-0.1, ang_max=0.1)
     ref = sl.match(grid, Scarp, scale=8, ages=[2.0, 9.0], ang_min=-0.1, ang_max=0.1)
     assert isinstance(sweep[8], tuple) and all(np.array_equal(a, b) for a, b in zip(sweep[8], ref))
+    sl.release()
 
 
 def test_results_of_one_plan_never_alias(emu_lib):

@@ -120,7 +120,7 @@ def test_header_symbols_exported_by_library():
     lib = ctypes.CDLL(_lib.library_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert ctypes.sizeof(_lib.SbTemplate) == 8 * 8 + 12 * 4
+    assert ctypes.sizeof(_lib.SbTemplate) == 8 * 8 + 14 * 4
     assert ctypes.sizeof(_lib.SbAngle) == 32
 
 
