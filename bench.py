@@ -4,11 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU algorithm
 
-Workload (BASELINE.json config 3, the 1-GPU case of the north-star search): Scarp,
-scale 100, 30 log-spaced ages (10^0..10^3.5) x 181 orientations (+-90 deg at 1 deg) on
-a seeded synthetic 4096 x 4096 DEM.  One "step" = the whole search = 9.11e10
-template-pixel evaluations.  With N > 1 ranks the orientation list is sharded across
-GPUs (strong scaling, total work fixed) and merged with two NCCL all-reduces.
+Default workload = BASELINE.json config 3 (the 1-GPU case of the north-star search): Scarp,
+scale 100, 30 log-spaced ages (10^0..10^3.5) x 181 orientations (+-90 deg at 1 deg) on a
+seeded synthetic 4096 x 4096 DEM.  One "step" = the whole search = 9.11e10 template-pixel
+evaluations.  With N > 1 ranks the orientation list is sharded across GPUs (strong scaling,
+total work fixed) and the best states are merged with one all-to-all of row bands.
+
+Other workloads (kept measurements, not the driver's line): ``--workload c1|c2|c4`` (the other
+single-GPU BASELINE configs), ``--workload ns`` (north-star: 16384^2, 30 ages x 181 angles,
+orientations sharded), ``--workload c5`` (32768^2, the same search, the raster sharded into row
+bands with halos: no data-path collective).  ``ns`` and ``c5`` generate their DEM on the device.
 
 Metric: template-pixel evaluations per second (Mpx-evals/s).
 """
@@ -28,21 +33,48 @@ sys.path.insert(0, ROOT)
 METRIC = "template_pixel_evals_per_sec"
 UNIT = "Mpx-evals/s"
 
+WORKLOADS = {
+    "c1": dict(n=1024, seed=0, template="Scarp", scales=[100.0], ages=[10.0], relief=30.0, shard="orientations",
+               label="C1: sl.match Scarp scale=100 age=10"),
+    "c2": dict(n=3601, seed=1, template="Channel", scales=[10.0], ages=[0.1], relief=300.0, shard="orientations",
+               label="C2: sl.match Channel scale=10 age=0.1 (pixel units, SRTM-like relief)"),
+    "c3": dict(n=4096, seed=2, template="Scarp", scales=[100.0], ages=30, relief=30.0, shard="orientations",
+               label="C3: calculate_best_fit_parameters Scarp scale=100, 30 log-spaced ages (10^0-10^3.5)"),
+    "c4": dict(n=8192, seed=3, template="Scarp", scales=[25.0, 50.0, 100.0, 200.0], ages=[10.0], relief=30.0,
+               shard="orientations", label="C4: multi-scale Scarp sweep (scale 25/50/100/200) age=10, one sweep"),
+    "ns": dict(n=16384, seed=4, template="Scarp", scales=[100.0], ages=30, relief=30.0, shard="orientations",
+               device_dem=True, label="north-star: Scarp scale=100, 30 log-spaced ages"),
+    "c5": dict(n=32768, seed=4, template="Scarp", scales=[100.0], ages=30, relief=30.0, shard="rows",
+               device_dem=True, label="C5: regional DEM in row bands with halos, Scarp scale=100, 30 log-spaced ages"),
+}
+
 
 def workload(args):
-    ages = np.logspace(0, 3.5, args.ages) if args.ages > 1 else np.array([10.0])
-    return {"n": args.size, "seed": 2, "scale": 100.0, "ages": ages,
-            "ang_min": -np.pi / 2, "ang_max": np.pi / 2}
+    wl = dict(WORKLOADS[args.workload])
+    if args.size:
+        wl["n"] = args.size
+    if args.ages:
+        wl["ages"] = args.ages
+    if args.shard:
+        wl["shard"] = args.shard
+    a = wl["ages"]
+    wl["ages"] = (np.logspace(0, 3.5, a) if a > 1 else np.array([10.0])) if isinstance(a, int) else np.asarray(a, float)
+    wl["ang_min"], wl["ang_max"] = -np.pi / 2, np.pi / 2
+    wl["name"] = args.workload
+    return wl
 
 
-def config_dict(args, wl, n_angles, extra=None):
-    cfg = {"workload": "C3: calculate_best_fit_parameters Scarp scale=100, %d log-spaced ages "
-                       "(10^0-10^3.5) x %d angles on a synthetic %dx%d DEM (seed %d)"
-                       % (len(wl["ages"]), n_angles, wl["n"], wl["n"], wl["seed"]),
-           "size": wl["n"], "n_ages": int(len(wl["ages"])), "n_angles": int(n_angles),
-           "template": "Scarp", "scale": wl["scale"],
-           "px_evals_per_step": int(wl["n"]) ** 2 * int(len(wl["ages"])) * int(n_angles),
-           "l2": "working set per step (>= 16 GB of spectra and intermediates) exceeds the 126 MB L2; no flush needed"}
+def px_evals(wl, n_angles):
+    return int(wl["n"]) ** 2 * len(wl["ages"]) * int(n_angles) * len(wl["scales"])
+
+
+def config_dict(wl, n_angles, extra=None):
+    cfg = {"workload": "%s x %d angles on a synthetic %dx%d DEM (seed %d)"
+                       % (wl["label"], n_angles, wl["n"], wl["n"], wl["seed"]),
+           "size": wl["n"], "n_ages": int(len(wl["ages"])), "n_angles": int(n_angles), "scales": list(wl["scales"]),
+           "template": wl["template"], "px_evals_per_step": px_evals(wl, n_angles),
+           "l2": "working set per step (>= 16 GB of spectra and intermediates at C3) exceeds the 126 MB L2; "
+                 "no flush needed"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -117,7 +149,7 @@ def _cpu_worker_count(n):
     return max(1, min(cores, int(avail * 0.6 // per_worker)))
 
 
-def cpu_reference_sample(z, scale, ages, angles, workers):
+def cpu_reference_sample(z, kind, scale, ages, angles, workers):
     """The reference's own flow for the sample: Pool fan-out over orientations at each
     age, ordered imap, parent-side compare (core.py:139-195, 266-294), NumPy/pocketfft in
     place of numexpr/pyfftw.  Returns (px_evals, seconds)."""
@@ -129,12 +161,28 @@ def cpu_reference_sample(z, scale, ages, angles, workers):
     stacks = []
     with mp.Pool(processes=workers) as pool:
         for age in ages:
-            work = partial(O.match_template, z, 1.0, 1.0, O.SCARP, scale, age)
+            work = partial(O.match_template, z, 1.0, 1.0, kind, scale, age)
             best = O.compare(pool.imap(work, angles, chunksize=1), ny, nx)
             stacks.append(np.stack(best))
     O.compare(stacks, ny, nx)
     dt = time.perf_counter() - t0
     return ny * nx * len(ages) * len(angles), dt
+
+
+def _oracle_kind(wl):
+    from oracle import scarplet_oracle as O
+    return O.SCARP if wl["template"] == "Scarp" else O.RICKER
+
+
+def _cpu_sample(wl, angles_all, z):
+    """Bounded sample of the workload: one orientation per worker at the middle age / first scale."""
+    n = wl["n"]
+    workers = _cpu_worker_count(n)
+    sel = np.linspace(0, len(angles_all) - 1, min(workers, len(angles_all))).astype(int)
+    ages = wl["ages"][len(wl["ages"]) // 2: len(wl["ages"]) // 2 + 1]
+    sample = "%d orientations x %d age of the %dx%d search per step (extrapolates linearly)" % (
+        len(sel), len(ages), n, n)
+    return workers, angles_all[sel], ages, sample
 
 
 def run_reference(args):
@@ -144,29 +192,25 @@ def run_reference(args):
     from scarplet_b200.synth import synthetic_dem
     from scarplet_b200 import params as P
     wl = workload(args)
+    if wl.get("device_dem"):
+        wl["n"] = 4096          # the CPU arm cannot hold the large rasters: same search on a 4096^2 sample
     angles_all = P.search_angles(wl["ang_min"], wl["ang_max"])
     n = wl["n"]
-    z = synthetic_dem(n, wl["seed"])
-    workers = _cpu_worker_count(n)
-    # bounded sample of the same workload: one orientation per worker at one age
-    sel = np.linspace(0, len(angles_all) - 1, min(workers, len(angles_all))).astype(int)
-    angles = angles_all[sel]
-    ages = wl["ages"][len(wl["ages"]) // 2: len(wl["ages"]) // 2 + 1]
+    z = synthetic_dem(n, wl["seed"], relief=wl["relief"])
+    workers, angles, ages, sample = _cpu_sample(wl, angles_all, z)
     times = []
     evals = 0
     for it in range(args.warmup + args.steps):
-        evals, dt = cpu_reference_sample(z, wl["scale"], ages, angles, workers)
+        evals, dt = cpu_reference_sample(z, _oracle_kind(wl), wl["scales"][0], ages, angles, workers)
         if it >= args.warmup:
             times.append(dt)
     sec = float(np.mean(times))
     value = evals / sec / 1e6
-    sample = "%d orientations x %d age of the %dx%d search per step (extrapolates linearly)" % (
-        len(angles), len(ages), n, n)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, wl, len(angles_all), {"sample": sample}),
+            "config": config_dict(wl, len(angles_all), {"sample": sample}),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                              "sample": sample,
                              "note": "oracle port of scarplet/core.py (NumPy/pocketfft standing in for "
@@ -177,16 +221,88 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------
+# device-side DEM for the rasters the host generator cannot hold
+# ---------------------------------------------------------------------------
+def device_dem_rows(n, seed, row0, nrows, device, relief=30.0, tile=4096):
+    """Rows ``(row0 + arange(nrows)) mod n`` of a seeded n x n DEM, float64 on ``device``.
+
+    SURVEY 8d's recipe at scale: a ``tile``^2 spectral-synthesis fractal (amplitude ~ k^-2.5,
+    zero DC, sigma = relief) repeated over the raster and modulated by a smooth amplitude field
+    that does not share its period (no two repeats are alike, nothing is mirrored), + 650 m +
+    0.02 x regional tilt + one diffused scarp 1.5 erf(x_rot / (2 sqrt(10))) at 0.3 rad + white
+    noise sigma = 0.03 m drawn per 256-row block from its own seeded generator (any band of rows
+    is reproducible on any rank), rounded to float32 like a GDAL Float32 raster (dem.py:317)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    t = min(tile, n)
+    ky = torch.fft.fftfreq(t, device=device)[:, None]
+    kx = torch.fft.rfftfreq(t, device=device)[None, :]
+    k = torch.sqrt(kx ** 2 + ky ** 2)
+    k[0, 0] = 1
+    spec = torch.complex(torch.randn(k.shape, generator=g, device=device), torch.randn(k.shape, generator=g, device=device))
+    spec = spec * k ** -2.5
+    spec[0, 0] = 0
+    base = torch.fft.irfft2(spec, s=(t, t))
+    base = (relief * base / base.std()).to(torch.float32)
+    del spec, k
+    rows = (row0 + torch.arange(nrows, device=device)) % n
+    cols = torch.arange(n, device=device)
+    z = base[rows % t][:, cols % t].to(torch.float64)
+    yy = rows.to(torch.float64)[:, None]
+    xx = cols.to(torch.float64)[None, :]
+    amp = 1.0 + 0.25 * torch.sin(2 * np.pi * yy / (0.37 * n) + 1.3) * torch.cos(2 * np.pi * xx / (0.41 * n) + 0.7)
+    z *= amp
+    del amp
+    c = (n - 1) / 2.0
+    xr = (xx - c) * np.cos(0.3) + (yy - c) * np.sin(0.3)
+    z += 650.0 + 0.02 * xx + 1.5 * torch.erf(xr / (2 * np.sqrt(10.0)))
+    del xr
+    blk = 256
+    for b in sorted(set((rows // blk).tolist())):
+        gb = torch.Generator(device=device)
+        gb.manual_seed(int(seed) * 1000003 + int(b))
+        noise = torch.randn((blk, n), generator=gb, device=device, dtype=torch.float32)
+        sel = (rows // blk) == b
+        z[sel] += 0.03 * noise[(rows[sel] % blk)].to(torch.float64)
+    return z.to(torch.float32).to(torch.float64).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# roofline bookkeeping
+# ---------------------------------------------------------------------------
+def algorithmic_bytes(kernel, tpa, batch):
+    """HBM bytes one template-pixel evaluation needs from each kernel of the complex64 schedule
+    (``tpa`` = templates per orientation, ``batch`` = templates per fold
+    launch).  Half spectra: a plane of Py x (Px/2+1) complex values is 4 B per pixel and field."""
+    if kernel == "k_curv_rows":
+        return (16.0 + 8.0) / tpa        # read dxx,dxy,dyy float4 (16), write both row spectra (8); once per angle
+    if kernel == "k_curv_cols":
+        return (8.0 + 8.0) / tpa         # read row spectra (8), write F[curv], F[curv^2] (8); once per angle
+    if kernel == "k_tmpl_rows":
+        return 0.6                       # the template's row spectra on its support rows only
+    if kernel == "k_conv_cols":
+        # write both inverse-column planes (8); the curvature-spectrum columns are staged in shared
+        # memory once per run of same-angle templates by the persistent kernel (8 / tpa), else per template
+        return 8.0 + (8.0 / tpa if tpa >= 4 else 8.0) + 0.6
+    if kernel == "k_fit_rows":
+        return 8.0 + 12.0 / max(batch, 1)    # read both planes (8) + best-state read-modify-write per launch
+    return 0.0
+
+
+def load_profile_counters():
+    """On-chip counters and DRAM bytes of the dominant kernels from the committed
+    ``ncu --set full`` capture of the benchmarked batch shape (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------
 # this repo's CUDA path
 # ---------------------------------------------------------------------------
-ALGO_BYTES = {
-    # algorithmic bytes per template-pixel evaluation of each per-template kernel
-    # (complex64 half spectra; DESIGN.md "byte model")
-    "k_conv_cols": 16.0,   # read F[curv], F[curv^2] (8) + write both inverse-column planes (8)
-    "k_fit_rows": 8.0,     # read both planes (8); best state amortised over the batch
-}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -194,7 +310,7 @@ def run_ours(args):
     from scarplet_b200.synth import synthetic_dem
     from scarplet_b200 import params as P
     from scarplet_b200.engine import Plan
-    from scarplet_b200.templates import Scarp
+    from scarplet_b200 import templates as T
     from scarplet_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,28 +329,56 @@ def run_ours(args):
 
     wl = workload(args)
     n = wl["n"]
+    spec = getattr(T, wl["template"])._sb_spec
     angles = P.search_angles(wl["ang_min"], wl["ang_max"])
-    ages = wl["ages"]
-    z = synthetic_dem(n, wl["seed"])
-    z_pinned = torch.from_numpy(z).pin_memory()
-    evals_per_step = n * n * len(ages) * len(angles)
-
+    ages, scales = wl["ages"], wl["scales"]
+    scale_arg = scales if len(scales) > 1 else scales[0]
+    evals_per_step = px_evals(wl, len(angles))
+    rows_mode = wl["shard"] == "rows"
     stream = torch.cuda.Stream(device=device)
     sampler = ClockSampler(local)
+
     with torch.cuda.stream(stream):
-        plan = Plan(n, n, 1.0, 1.0, device=local, stream=stream.cuda_stream)
+        # ---- plan and DEM ----------------------------------------------------------------
+        if rows_mode:
+            plan, (row_lo, row_hi) = D.spatial_plan(n, n, 1.0, 1.0, spec, scale_arg, ages, angles,
+                                                    device=local, stream=stream.cuda_stream, states=len(scales))
+        else:
+            plan = Plan(n, n, 1.0, 1.0, device=local, stream=stream.cuda_stream, states=len(scales))
+            row_lo, row_hi = 0, n
         if args.fast is not None:
             plan.set_option("fast", args.fast)
-        plan.set_dem(z_pinned.numpy())                       # inputs resident in HBM
-        lo, hi = D.shard_bounds(len(angles), world, rank)
-        a_rec, t_rec, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, wl["scale"], ages, angles,
-                                                         "age_major", angle_slice=(lo, hi))
+        r0, nrows = plan.dem_rows()
+        z = z_pinned = z_dev = None
+        if wl.get("device_dem"):
+            z_dev = device_dem_rows(n, wl["seed"], r0, nrows, device, relief=wl["relief"])
+            stream.synchronize()
+            plan.set_dem_device(z_dev.data_ptr())
+        else:
+            z = synthetic_dem(n, wl["seed"], relief=wl["relief"])
+            z_pinned = torch.from_numpy(np.take(z, (r0 + np.arange(nrows)) % n, axis=0) if nrows != n else z).pin_memory()
+            plan.set_dem(z_pinned.numpy())                       # inputs resident in HBM
+        if rows_mode:
+            D.share_dem_stats(plan, device=device)
+            lo, hi = 0, len(angles)
+        else:
+            lo, hi = D.shard_bounds(len(angles), world, rank)
+        a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, scale_arg, ages, angles, "age_major",
+                                                         angle_slice=(lo, hi))
+        merge_ms = []
 
-        def step():
+        def step(timed=False):
             plan.reset()
             plan.sweep(a_rec, t_rec)
-            if world > 1:
-                D.merge_best_state(plan, device)
+            if world > 1 and not rows_mode:
+                m0 = torch.cuda.Event(enable_timing=True)
+                m1 = torch.cuda.Event(enable_timing=True)
+                m0.record(stream)
+                for s in range(len(scales)):
+                    D.merge_best_bands(plan, device, state=s)
+                m1.record(stream)
+                if timed:
+                    merge_ms.append((m0, m1))
 
         def fence():
             stream.synchronize()
@@ -254,7 +398,7 @@ def run_ours(args):
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            step()
+            step(timed=True)
         e1.record(stream)
         fence()
         clocks = sampler.stop() if rank == 0 else None
@@ -263,45 +407,85 @@ def run_ours(args):
         plan.set_option("profile", 0)
         launches = plan.launches - launches0
         geo = plan.last_geometry()
+        fft_area = plan.fft_area
+        merge = float(np.mean([a.elapsed_time(b) for a, b in merge_ms])) if merge_ms else 0.0
 
-        t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
+        stats = torch.tensor([ms_total, merge, float(plan.device_bytes + torch.cuda.max_memory_allocated(device))],
+                             dtype=torch.float64, device=device)
         n_launch = torch.tensor([launches], dtype=torch.int64, device=device)
         if world > 1:
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
             dist.all_reduce(n_launch, op=dist.ReduceOp.SUM)
-        ms_step = float(t_ms.item()) / args.steps
+        ms_step = float(stats[0].item()) / args.steps
         value = evals_per_step / (ms_step * 1e-3) / 1e6
 
-        # ---- end to end through the public API with host buffers ---------------
-        def e2e_step():
-            plan.set_dem(z_pinned.numpy())                   # H2D inside the timed region
-            out = D.sharded_search(plan, Scarp._sb_spec, wl["scale"], ages, angles, "age_major",
-                                   device=device, finalize=(rank == 0))
-            return out
+        # ---- end to end through the public multi-GPU API with host buffers -------------------
+        # every rank: H2D of its DEM (whole raster, or its band), search, merge, decode and D2H of
+        # the row band it owns afterwards -- the distributed form of the (4, ny, nx) result
+        e2e = None
+        if not wl.get("device_dem"):
+            def e2e_step():
+                plan.set_dem(z_pinned.numpy())                   # H2D inside the timed region
+                if rows_mode:
+                    D.share_dem_stats(plan, device=device)
+                    return D.spatial_search(plan, spec, scale_arg, ages, angles)
+                return D.sharded_search(plan, spec, scale_arg, ages, angles, "age_major", device=device, merge="bands")
 
-        for _ in range(3):          # untimed: the plan's page-locked result pool fills (engine._result_array)
-            out = e2e_step()
-        fence()
-        t0 = time.perf_counter()
-        out = None
-        for _ in range(args.e2e_steps):
-            out = e2e_step()
-        fence()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e_value = evals_per_step / float(t_e2e.item()) / 1e6
-        h2d = int(z.nbytes) * world + sum(int(ctypes_sizeof(x)) for x in (a_rec[0], t_rec[0]))
-        d2h = int(out.nbytes) if out is not None else 0
+            for _ in range(3):      # untimed: the plan's page-locked result pool fills (engine._result_array)
+                out = e2e_step()
+            fence()
+            t0 = time.perf_counter()
+            out = None
+            for _ in range(args.e2e_steps):
+                out = e2e_step()
+            fence()
+            e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+            t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+            io = torch.tensor([int(z_pinned.numel() * 8) + ctypes_sizeof(a_rec[0]) + ctypes_sizeof(t_rec[0]),
+                               int(out[2].nbytes)], dtype=torch.int64, device=device)
+            if world > 1:
+                dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+                dist.all_reduce(io, op=dist.ReduceOp.SUM)
+            e2e = {"value": evals_per_step / float(t_e2e.item()) / 1e6, "unit": UNIT,
+                   "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+                   "ms_per_step": float(t_e2e.item()) * 1e3, "steps": args.e2e_steps,
+                   "api": "per rank: Plan.set_dem(host) + distributed.%s -> (row_lo, row_hi, (4, rows, nx) float64 on host); "
+                          "the ranks' row bands together are the (4, ny, nx) result"
+                          % ("spatial_search(...)" if rows_mode else "sharded_search(..., merge='bands')")}
+            del out
         plan.close()
+
+        # ---- the drop-in entry itself: sl.match(DEMGrid, ...) cold and warm (1 GPU) ---------
+        dropin = None
+        if world == 1 and not wl.get("device_dem") and not args.no_dropin:
+            import scarplet_b200 as sl
+            grid = sl.DEMGrid(z, 1.0)
+            cls = getattr(sl.WindowedTemplate, wl["template"])
+
+            def call():
+                if len(scales) > 1:
+                    return sl.match_scales(grid, cls, scales, age=float(ages[0]))
+                if len(ages) == 1:
+                    return sl.match(grid, cls, scale=scales[0], age=float(ages[0]))
+                return sl.match(grid, cls, scale=scales[0], ages=ages)
+            times = []
+            for _ in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                res = call()
+                times.append(time.perf_counter() - t0)
+                del res
+            sl.release()
+            dropin = {"api": "sl.match(DEMGrid, %s, ...) -> float64 stack(s) on host (plans cached per raster shape)" % wl["template"],
+                      "cold_ms": times[0] * 1e3, "warm_ms": float(np.mean(times[2:])) * 1e3,
+                      "warm_value": evals_per_step / float(np.mean(times[2:])) / 1e6, "unit": UNIT}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel -----------------------------------------
+    # ---- roofline: every kernel, three ways -------------------------------------------------
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -310,58 +494,75 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    per_template = {k: v for k, v in prof.items() if k in ALGO_BYTES and v[1] > 0}
-    dom = max(per_template, key=lambda k: per_template[k][0]) if per_template else "k_conv_cols"
-    dom_ms, dom_launches = prof.get(dom, (0.0, 0))
-    my_evals = n * n * len(ages) * (hi - lo) * args.steps       # rank 0's share
-    achieved = ALGO_BYTES[dom] * my_evals / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    # DRAM bytes of the same kernel from the committed `ncu --set full` capture
-    # (profiles/traffic.json, bytes per px-eval) scaled to this run's average launch
-    traffic = None
-    traffic_src = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f).get(dom)
-        if tj and dom_launches:
-            traffic = tj["dram_bytes_per_px_eval"] * my_evals / dom_launches
-            traffic_src = tj.get("source")
-    except Exception:
-        pass
-    total_kernel_ms = sum(v[0] for v in prof.values())
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
-                "achieved_bytes_per_launch": (ALGO_BYTES[dom] * my_evals / dom_launches) if dom_launches else None,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_px_eval": ALGO_BYTES[dom],
-                "avg_launch_ms": dom_ms / dom_launches if dom_launches else None,
-                "launches": dom_launches,
-                "share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
-                "whole_step_hbm_frac": (24.0 * my_evals / (total_kernel_ms * 1e-3) / 1e9 / peak)
-                if total_kernel_ms else None}
+    my_evals = int(n) * int(row_hi - row_lo) * len(ages) * (hi - lo) * len(scales) * args.steps   # rank 0's share
+    tpa = len(ages) * len(scales)
+    batch = max(1, geo["template_batch"])
+    counters = load_profile_counters()
+    per_kernel = {}
+    total_ms = sum(v[0] for v in prof.values())
+    total_bytes = 0.0
+    for k, (ms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        b = algorithmic_bytes(k, tpa, batch) * my_evals
+        total_bytes += b
+        entry = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
+                 "algorithmic_bytes_per_px_eval": algorithmic_bytes(k, tpa, batch),
+                 "algorithmic_GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                 "algorithmic_frac": b / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
+                 "share_of_step": ms / total_ms if total_ms else None}
+        c = counters.get(k)
+        if c and ms > 0:
+            dram = c["dram_bytes_per_px_eval"] * my_evals
+            entry.update({"dram_bytes_per_px_eval": c["dram_bytes_per_px_eval"],
+                          "dram_GBps": dram / (ms * 1e-3) / 1e9, "dram_frac": dram / (ms * 1e-3) / 1e9 / peak,
+                          "lsu_wavefront_pct": c.get("lsu_wavefront_pct"), "fp32_pipe_pct": c.get("fma_pipe_pct"),
+                          "issue_active_pct": c.get("issue_active_pct"), "counters_source": c.get("source")})
+        per_kernel[k] = entry
+    heavy = {k: v for k, v in per_kernel.items() if k in ("k_conv_cols", "k_fit_rows")}
+    dom = max(heavy, key=lambda k: heavy[k]["ms_per_step"]) if heavy else max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    d = per_kernel[dom]
+    dom_ms, dom_launches = prof[dom]
+    ab = algorithmic_bytes(dom, tpa, batch) * my_evals
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": d["algorithmic_frac"],
+                "traffic": (d["dram_bytes_per_px_eval"] * my_evals / dom_launches) if "dram_bytes_per_px_eval" in d else None,
+                "traffic_source": d.get("counters_source"),
+                "dram_frac": d.get("dram_frac"), "fp32_pipe_pct": d.get("fp32_pipe_pct"),
+                "lsu_wavefront_pct": d.get("lsu_wavefront_pct"),
+                "achieved_bytes_per_launch": ab / dom_launches if dom_launches else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_px_eval": algorithmic_bytes(dom, tpa, batch),
+                "avg_launch_ms": dom_ms / dom_launches if dom_launches else None, "launches": dom_launches,
+                "share_of_step": d["share_of_step"],
+                "whole_step": {"algorithmic_bytes_per_px_eval": total_bytes / my_evals if my_evals else None,
+                               "algorithmic_frac": total_bytes / (total_ms * 1e-3) / 1e9 / peak if total_ms else None,
+                               "kernel_ms_per_step": total_ms / args.steps},
+                "kernels": per_kernel,
+                "note": "frac = algorithmic bytes / CUDA-event time / measured copy peak; dram_frac = DRAM bytes of the "
+                        "committed ncu capture scaled to this run / the same time; the binding resource of both heavy "
+                        "kernels is on-chip (FP32 pipe and shared-memory wavefronts), see fp32_pipe_pct / lsu_wavefront_pct"}
 
-    # ---- CPU baseline: oracle port on this host's cores, bounded sample --------------
+    # ---- CPU baseline: oracle port on this host's cores, bounded sample --------------------------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        workers = _cpu_worker_count(n)
-        sel = np.linspace(0, len(angles) - 1, min(workers, len(angles))).astype(int)
-        c_ages = ages[len(ages) // 2: len(ages) // 2 + 1]
-        evals, dt = cpu_reference_sample(z, wl["scale"], c_ages, angles[sel], workers)
+    if world == 1 and not args.no_cpu_baseline and z is not None:
+        workers, c_angles, c_ages, sample = _cpu_sample(wl, angles, z)
+        evals, dt = cpu_reference_sample(z, _oracle_kind(wl), scales[0], c_ages, c_angles, workers)
         cpu = {"value": evals / dt / 1e6, "unit": UNIT, "cores": workers, "kind": "port",
-               "sample": "%d orientations x 1 age of the %dx%d search, %.1f s" % (len(sel), n, n, dt)}
+               "sample": "%s, %.1f s" % (sample, dt)}
 
+    area = float(row_hi - row_lo) * n
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, wl, len(angles), {"parallelism": "orientations sharded over %d GPU(s)" % world,
-                                                         "fft_domain": [geo["Py"], geo["Px"]],
-                                                         "tiles": [geo["tiles_y"], geo["tiles_x"]],
-                                                         "batches": [geo["angle_batch"], geo["template_batch"]]}),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t_e2e.item()) * 1e3, "steps": args.e2e_steps,
-                    "api": "Plan.set_dem(host) + distributed.sharded_search(...) -> (4,ny,nx) float64 on host"},
+            "config": config_dict(wl, len(angles), {
+                "parallelism": ("raster sharded into %d row band(s) with halos" if rows_mode
+                                else "orientations sharded over %d GPU(s)") % world,
+                "fft_domain_max": [geo["Py"], geo["Px"]], "tiles": [geo["tiles_y"], geo["tiles_x"]],
+                "fft_area_over_raster_area": fft_area / area if area else None,
+                "batches": [geo["angle_batch"], geo["template_batch"]]}),
+            "clocks": clocks, "e2e": e2e, "e2e_dropin": dropin,
             "gpu_launches": int(n_launch.item()),
+            "merge_ms_per_step": float(stats[1].item()), "device_gb_per_rank_max": float(stats[2].item()) / 1e9,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
@@ -380,10 +581,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=4096)
-    ap.add_argument("--ages", type=int, default=30)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default=None, choices=["orientations", "rows"])
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--ages", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--fast", type=int, default=None, help="developer switch: 0 = simple kernels")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -234,15 +234,15 @@ def match_template(z, dx, dy, kind, scale, age, angle):
     return amp, age, angle, snr
 
 
-def match_template_plugin(z, dx, dy, Template, scale, age, angle, **kwargs):
+def match_template_plugin(z, grid_dx, grid_dy, Template, scale, age, angle, **kwargs):
     """core.py:339-375 for ANY template class -- the plugin surface of the path: a class
     callable as ``Template(scale, age, angle, nx, ny, de)`` (core.py:345) with
     ``template()`` (:346), ``get_window_limits()`` (:373) and optionally ``get_err_mask()``
     (:369-371).  Same arithmetic as ``match_template`` above."""
     fft2, ifft2, fftshift = np.fft.fft2, np.fft.ifft2, np.fft.fftshift
-    curv = directional_laplacian(z, dx, dy, angle)           # :340
+    curv = directional_laplacian(z, grid_dx, grid_dy, angle)   # :340
     ny, nx = curv.shape
-    template_obj = Template(scale, age, angle, nx, ny, dx, **kwargs)   # :343-345
+    template_obj = Template(scale, age, angle, nx, ny, grid_dx, **kwargs)   # :343-345 (kwargs may hold dx, dy)
     t = template_obj.template()                              # :346
     M = t != 0                                               # :348
     fm2 = fft2(M)
@@ -359,3 +359,83 @@ def calculate_best_fit_parameters_serial(z, dx, dy, kind, scale,
     angles = search_angles(ang_min, ang_max)
     return compare((match_template(z, dx, dy, kind, scale, age, angle)
                     for angle in angles for age in ages), ny, nx)
+
+
+def calculate_best_fit_parameters_serial_plugin(z, grid_dx, grid_dy, Template, scale, ang_max=np.pi / 2,
+                                                ang_min=-np.pi / 2, ages=None, **kwargs):
+    """core.py:65-136 with a plugin class: flat angle-outer / age-inner sweep, keyword
+    arguments forwarded to the template's constructor (core.py:116-121)."""
+    ny, nx = z.shape
+    ages = default_ages() if ages is None else ages
+    return compare((match_template_plugin(z, grid_dx, grid_dy, Template, scale, age, angle, **kwargs)
+                    for angle in search_angles(ang_min, ang_max) for age in ages), ny, nx)
+
+
+# ---------------------------------------------------------------------------
+# dem.py, either side of the match path (SURVEY.md 8f-3, 8f-4)
+# ---------------------------------------------------------------------------
+
+def estimate_curvature_noiselevel(z, dx, dy, sigma=100):
+    """``CalculationMixin._estimate_curvature_noiselevel`` (dem.py:152-179): for 180
+    directions, mean and standard deviation of the directional Laplacian minus its Gaussian
+    low-pass.  ``sigma`` is 100 in the reference (dem.py:172); a parameter here so that small
+    test rasters exercise the reflecting boundary the same way."""
+    from scipy import ndimage                                # dem.py:164
+    angles = np.linspace(0, np.pi, num=180)                  # :166
+    mean, sd = [], []
+    z = np.array(z, dtype=np.float64)
+    for alpha in angles:                                     # :171-175
+        del2z = directional_laplacian(z, dx, dy, alpha)
+        # the reference's Laplacian zero-fills NaN cells of the grid IN PLACE (dem.py:85-86), so
+        # only the first direction sees them (as NaN, :105); the other 179 see zeros
+        z[np.isnan(z)] = 0
+        lowpass = ndimage.gaussian_filter(del2z, sigma)
+        highpass = del2z - lowpass
+        with np.errstate(all='ignore'):
+            mean.append(np.nanmean(highpass))
+            sd.append(np.nanstd(highpass))
+    return angles, mean, sd
+
+
+def fill_nodata_pass(z, max_search_distance):
+    """One pass of the nodata fill that stands in for ``rasterio.fill.fillnodata``
+    (dem.py:406-408; rasterio / GDAL are not installable here, so this restates the
+    REPLACEMENT the CUDA path defines, not GDAL's algorithm -- parity with GDAL unpinned): a
+    NaN cell becomes the inverse-distance-weighted mean of the nearest valid cell along each
+    of the eight row / column / diagonal rays within ``max_search_distance`` cells."""
+    ny, nx = z.shape
+    out = z.copy()
+    rays = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]
+    for r, c in np.argwhere(np.isnan(z)):
+        wsum = vsum = 0.0
+        for dr, dc in rays:
+            step = 1.4142135623730951 if dr and dc else 1.0
+            s = 1
+            while s * step <= max_search_distance:
+                rr, cc = r + s * dr, c + s * dc
+                if rr < 0 or rr >= ny or cc < 0 or cc >= nx:
+                    break
+                v = z[rr, cc]
+                if v == v:
+                    w = 1.0 / (s * step)
+                    wsum += w
+                    vsum += w * v
+                    break
+                s += 1
+        if wsum > 0:
+            out[r, c] = vsum / wsum
+    return out
+
+
+def fill_nodata(z):
+    """``DEMGrid._fill_nodata`` (dem.py:388-414): passes with the reference's search distance
+    (half of the longest per-row / per-column nodata count, :403-405) until no NaN is left
+    (:402)."""
+    z = np.array(z, dtype=np.float64)
+    num, prev = int(np.isnan(z).sum()), None
+    while num > 0 and num != prev:
+        mask = np.isnan(z)
+        dist = max(mask.sum(axis=1).max(), mask.sum(axis=0).max()) / 2
+        z = fill_nodata_pass(z, max(dist, 1.0))
+        prev, num = num, int(np.isnan(z).sum())
+    return z

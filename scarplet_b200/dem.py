@@ -64,20 +64,35 @@ class DEMGrid(object):
         moments; the 180 directions are quadratic forms of those (instead of 180 Laplacians
         and 180 filters)."""
         angles = np.linspace(0, np.pi, num=180)                      # dem.py:166
+        z = self._griddata
+        has_nan = bool(np.isnan(z).any())
         with self._plan() as plan:
-            plan.set_dem(self._griddata)
-            m = plan.curvature_noise_moments(sigma, truncate)
-        cnt = m[0]
-        if cnt <= 0:
-            nan = [float("nan")] * len(angles)
-            return angles, list(nan), list(nan)
-        s_xx, s_xy, s_yy, q_xx, q_xy, q_yy, q_xx_xy, q_xx_yy, q_xy_yy = m[1:] / cnt
-        c2, s2 = np.cos(angles) ** 2, np.sin(angles) ** 2            # dem.py:103-104
-        sc = 2 * np.sin(angles) * np.cos(angles)
-        mean = s_xx * c2 - s_xy * sc + s_yy * s2
-        second = (q_xx * c2 ** 2 + q_xy * sc ** 2 + q_yy * s2 ** 2
-                  - 2 * q_xx_xy * c2 * sc + 2 * q_xx_yy * c2 * s2 - 2 * q_xy_yy * sc * s2)
-        sd = np.sqrt(np.maximum(second - mean ** 2, 0.0))
+            plan.set_dem(z)
+            moments = [plan.curvature_noise_moments(sigma, truncate)]
+            if has_nan:
+                # The reference's Laplacian zero-fills nodata cells of the grid in place on its
+                # first call (dem.py:85-86): only the first direction sees them as NaN
+                # (dem.py:105), the other 179 see zeros.  Same values here, grid untouched.
+                plan.set_dem(np.where(np.isnan(z), 0.0, z))
+                moments.append(plan.curvature_noise_moments(sigma, truncate))
+
+        def stats(m, ang):
+            if m[0] <= 0:
+                nan = np.full(len(ang), np.nan)
+                return nan, nan
+            s_xx, s_xy, s_yy, q_xx, q_xy, q_yy, q_xx_xy, q_xx_yy, q_xy_yy = m[1:] / m[0]
+            c2, s2 = np.cos(ang) ** 2, np.sin(ang) ** 2              # dem.py:103-104
+            sc = 2 * np.sin(ang) * np.cos(ang)
+            mean = s_xx * c2 - s_xy * sc + s_yy * s2
+            second = (q_xx * c2 ** 2 + q_xy * sc ** 2 + q_yy * s2 ** 2
+                      - 2 * q_xx_xy * c2 * sc + 2 * q_xx_yy * c2 * s2 - 2 * q_xy_yy * sc * s2)
+            return mean, np.sqrt(np.maximum(second - mean ** 2, 0.0))
+
+        mean, sd = stats(moments[-1], angles)
+        if has_nan:
+            m0, s0 = stats(moments[0], angles[:1])
+            mean = np.concatenate([m0, mean[1:]])
+            sd = np.concatenate([s0, sd[1:]])
         return angles, [float(v) for v in mean], [float(v) for v in sd]
 
     def _fill_nodata(self):

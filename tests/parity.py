@@ -105,8 +105,11 @@ def stack_report(res, ref, odd_template=True, ref_age_stacks=None, ages=None):
     return out
 
 
-def assert_parity(rep, frac=FRAC_OVER_TOL, agreement=INDEX_AGREEMENT, explain=True, tie_share=3e-3):
-    """The north_star tolerances as bounds (module docstring)."""
+def assert_parity(rep, frac=None, agreement=INDEX_AGREEMENT, explain=True, tie_share=3e-3):
+    """The north_star tolerances as bounds (module docstring).  ``frac`` defaults to
+    FRAC_OVER_TOL, but never fewer than three pixels of a small raster."""
+    if frac is None:
+        frac = max(FRAC_OVER_TOL, 3.0 / max(rep["valid"], 1))
     assert rep["mask_mismatch_unexplained"] == 0, rep
     assert rep["tie_reset_pixels"] <= max(3, int(tie_share * rep["valid"])), rep
     assert rep["index_agreement"] >= agreement, rep

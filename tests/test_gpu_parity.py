@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from tests.parity import AMP_SNR_RTOL, INDEX_AGREEMENT, stack_report
+from tests.parity import AMP_SNR_RTOL, INDEX_AGREEMENT, assert_parity, save_report, stack_report
 
 pytestmark = pytest.mark.gpu
 
@@ -204,9 +204,9 @@ def test_search_reference_run(cuda_lib, golden):
     grid = sl.DEMGrid(golden.seeded_dem("a"), info["de"])
     res = sl.calculate_best_fit_parameters(grid, Scarp, info["scale"], info["age"])
     rep = stack_report(res, golden.npz("reference_runs.npz")["search_a"])
-    assert rep["mask_mismatch_unexplained"] == 0 and rep["tie_reset_pixels"] <= 5, rep
-    assert rep["index_agreement"] >= INDEX_AGREEMENT, rep
-    assert rep["frac_snr_over_tol"] <= 2e-3, rep
+    save_report("reference_run_search_a", rep)
+    assert rep["tie_reset_pixels"] <= 5, rep
+    assert_parity(rep)
 
 
 def test_compare_exact_semantics(cuda_lib, golden):
@@ -235,10 +235,8 @@ def test_search_vs_oracle(cuda_lib, shape, tmpl, scale, age):
     res = sl.calculate_best_fit_parameters(sl.DEMGrid(z, 1.0), cls, scale, age)
     ref = O.calculate_best_fit_parameters(z, 1.0, 1.0, kind, scale, age, processes=8)
     rep = stack_report(res, ref, odd_template=(kind != O.RICKER))
-    assert rep["mask_mismatch_unexplained"] == 0, rep
-    assert rep["tie_reset_pixels"] <= max(3, int(2e-3 * rep["valid"])), rep
-    assert rep["index_agreement"] >= INDEX_AGREEMENT, rep
-    assert rep["frac_snr_over_tol"] <= 1e-3 and rep["frac_amp_over_tol"] <= 2e-3, rep
+    save_report("search_vs_oracle_%s_%dx%d" % (tmpl, shape[0], shape[1]), rep)
+    assert_parity(rep)
 
 
 def test_tiled_equals_single_domain(cuda_lib):
@@ -265,7 +263,7 @@ def test_tiled_equals_single_domain(cuda_lib):
     rep = stack_report(outs[1], outs[0])
     assert rep["mask_equal"], rep
     assert rep["index_agreement"] >= 0.9995, rep
-    assert rep["snr_rel_p50"] < 1e-5, rep
+    assert rep["snr_rel_p50"] < 1e-5 and rep["snr_rel_max_strong"] <= AMP_SNR_RTOL, rep
 
 
 def test_large_raster_properties(cuda_lib):
@@ -292,8 +290,9 @@ def test_large_raster_properties(cuda_lib):
     sub = res[:, c0 + m:c0 + size - m, c0 + m:c0 + size - m]
     rsub = ref[:, m:size - m, m:size - m]
     rep = stack_report(sub, rsub)
-    assert rep["valid"] > 10000 and rep["index_agreement"] >= INDEX_AGREEMENT, rep
-    assert rep["frac_snr_over_tol"] <= 1e-3, rep
+    save_report("c3_single_age_crop", rep)
+    assert rep["valid"] > 10000
+    assert_parity(rep)
 
 
 @pytest.mark.parametrize("shape", [(256, 256), (300, 210)])
@@ -317,9 +316,7 @@ def test_plugin_template_generic_path(cuda_lib, shape):
     res = sl.calculate_best_fit_parameters(sl.DEMGrid(z, 1.0), Ridge, 12, 2.0, ang_max=0.2, ang_min=-0.2)
     ref = O.calculate_best_fit_parameters_plugin(z, 1.0, 1.0, Ridge, 12, 2.0, ang_max=0.2, ang_min=-0.2)
     rep = stack_report(res, ref, odd_template=False)
-    assert rep["mask_mismatch_unexplained"] == 0, rep
-    assert rep["index_agreement"] >= INDEX_AGREEMENT, rep
-    assert rep["frac_snr_over_tol"] <= 1e-3 and rep["frac_amp_over_tol"] <= 2e-3, rep
+    assert_parity(rep)
 
 
 @pytest.mark.parametrize("shape", [(256, 256), (200, 333)])
@@ -355,11 +352,15 @@ def test_match_scales(cuda_lib):
     multi = sl.match_scales(grid, Scarp, [10, 20, 40], age=10.0)
     assert sorted(multi) == [10, 20, 40]
     for scale in (10, 40):
-        assert np.array_equal(multi[scale], sl.match(grid, Scarp, scale=scale, age=10.0))
+        single = sl.match(grid, Scarp, scale=scale, age=10.0)
+        # one sweep for all scales: the shared FFT domain is sized for the largest, so the
+        # values agree with the per-scale search to rounding, masks and indices exactly
+        assert np.array_equal(multi[scale][3] > 0, single[3] > 0)
+        rep = stack_report(multi[scale], single)
+        assert rep["index_agreement"] >= 0.9999 and rep["snr_rel_max_strong"] < 2e-5, rep
         ref = O.calculate_best_fit_parameters(z, 1.0, 1.0, O.SCARP, scale, 10.0, processes=8)
         rep = stack_report(multi[scale], ref)
-        assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= INDEX_AGREEMENT, rep
-        assert rep["frac_snr_over_tol"] <= 1e-3, rep
+        assert_parity(rep)
 
 
 def test_results_of_one_plan_never_alias(cuda_lib):

@@ -74,3 +74,28 @@ def test_plugin_template_identical(ref):
     res = sl.calculate_best_fit_parameters(grid, Ridge, 7, 1.5, ang_max=0.1, ang_min=-0.1)
     ores = O.calculate_best_fit_parameters_plugin(z, 1.0, 1.0, Ridge, 7, 1.5, ang_max=0.1, ang_min=-0.1)
     assert np.array_equal(res, ores)
+
+
+def test_serial_sweep_forwards_kwargs_identical(ref):
+    """core.py:116-121: keyword arguments reach the template's constructor in the serial sweep."""
+    sl, WT = ref
+    z = _dem(40, 48, 2)
+    grid = ref_import.make_grid(z, 1.0, 1.0)
+    ser = sl.calculate_best_fit_parameters_serial(grid, WT.ShiftedLeftFacingUpperBreakScarp, 6,
+                                                  ang_max=0.01, ang_min=-0.01, dx=3, dy=2)
+    oser = O.calculate_best_fit_parameters_serial_plugin(z, 1.0, 1.0, WT.ShiftedLeftFacingUpperBreakScarp, 6,
+                                                         ang_max=0.01, ang_min=-0.01, dx=3, dy=2)
+    for a, b in zip(ser, oser):
+        assert np.array_equal(a, b)
+
+
+def test_curvature_noiselevel_identical(ref):
+    """dem.py:152-179 of the unmodified reference (sigma 100 is hard-coded there, so the raster
+    is small and the filter runs on its reflecting boundary throughout)."""
+    z = _dem(30, 36, 4)
+    z[7, 9] = np.nan
+    grid = ref_import.make_grid(z.copy(), 2.0, 2.0)
+    angles, mean, sd = grid._estimate_curvature_noiselevel()
+    oangles, omean, osd = O.estimate_curvature_noiselevel(z, 2.0, 2.0, sigma=100)
+    assert np.array_equal(angles, oangles)
+    assert np.array_equal(mean, omean, equal_nan=True) and np.array_equal(sd, osd, equal_nan=True)
