@@ -196,8 +196,13 @@ int sb_curvature_noise_moments(sb_plan* plan, double sigma, double truncate, dou
  * *remaining = cells still NaN. */
 int sb_fill_nodata(sb_plan* plan, double* dem_host_inout, double max_search_distance, long* remaining);
 
-/* unit-test hook: batched complex64 FFT of length n (power of two, 64..8192) over rows */
+/* unit-test hook: batched complex64 FFT of length n (power of two, 128..8192) over rows;
+ * inverse: bit 0 = inverse transform, bit 1 = use the radix-64 core (n = 4096 only) */
 int sb_debug_fft(sb_plan* plan, int n, int rows, const float* in_host, float* out_host, int inverse);
+
+/* developer hook: device time (ms per launch, CUDA events) of the batched FFT kernel alone on
+ * resident data; radix64 != 0 selects the 64 x 64 core (n = 4096) */
+int sb_debug_fft_bench(sb_plan* plan, int n, int rows, int reps, int radix64, float* ms_per_launch);
 
 /* synchronise the plan's stream */
 int sb_sync(sb_plan* plan);

@@ -12,6 +12,7 @@
 #include "sb_kernels.cuh"
 #include "sb_fast.cuh"
 #include "sb_aux.cuh"
+#include "sb_r64.cuh"
 
 static_assert(sizeof(sb_template) == sizeof(sb::Tmpl), "sb_template / sb::Tmpl layout");
 static_assert(sizeof(sb_angle) == sizeof(sb::Angle), "sb_angle / sb::Angle layout");
@@ -167,6 +168,21 @@ int twiddles(sb_plan* pl, int n, const typename Vec<R>::v2** out) {
     SB_TRY(sb_rt_sync(pl->stream));
     pl->tw[key] = d;
     *out = (const C2*)d;
+    return 0;
+}
+
+// table of the radix-64 core (sb_r64.cuh), key -64
+int twiddles64(sb_plan* pl, const float2** out) {
+    auto it = pl->tw.find(-64);
+    if (it != pl->tw.end()) { *out = (const float2*)it->second; return 0; }
+    std::vector<float2> host((size_t)sb64::kTwRows * sb64::R);
+    sb64::fill_twiddles64(host.data());
+    void* d = nullptr;
+    SB_TRY(sb_rt_malloc(&d, host.size() * sizeof(float2)));
+    SB_TRY(sb_rt_h2d(d, host.data(), host.size() * sizeof(float2), pl->stream));
+    SB_TRY(sb_rt_sync(pl->stream));
+    pl->tw[-64] = d;
+    *out = (const float2*)d;
     return 0;
 }
 
@@ -1327,6 +1343,19 @@ int sb_debug_fft(sb_plan* pl, int n, int rows, const float* in_host, float* out_
     float2* d_in = (float2*)pl->raw.p;
     float2* d_out = d_in + (size_t)rows * n;
     SB_TRY(sb_rt_h2d(d_in, in_host, bytes, pl->stream));
+    if (inverse & 2) {          // the radix-64 core (length 4096 only)
+        if (n != sb64::N) return fail("sb_debug_fft: the radix-64 core is length 4096");
+        const float2* tw64 = nullptr;
+        SB_OK(twiddles64(pl, &tw64));
+        constexpr size_t smem = (size_t)(4 * sb64::kXchg + sb64::kTwRows * sb64::R) * sizeof(float2);
+        SB_ALLOW_SMEM(sb64::k_fft4096_r64, smem);
+        SB_LAUNCH(sb64::k_fft4096_r64, dim3(div_up(rows, 4)), dim3(256), smem, pl->stream, rows, (const float2*)d_in,
+                  d_out, inverse & 1, tw64);
+        SB_OK(check_launch(pl, "k_fft4096_r64"));
+        SB_TRY(sb_rt_d2h(out_host, d_out, bytes, pl->stream));
+        SB_TRY(sb_rt_sync(pl->stream));
+        return 0;
+    }
     SB_OK(dispatch_n(n, [&](auto nn) {
         constexpr int N = decltype(nn)::value;
         using S = Shape<N, float>;
@@ -1339,6 +1368,55 @@ int sb_debug_fft(sb_plan* pl, int n, int rows, const float* in_host, float* out_
     SB_TRY(sb_rt_d2h(out_host, d_out, bytes, pl->stream));
     SB_TRY(sb_rt_sync(pl->stream));
     return 0;
+}
+
+int sb_debug_fft_bench(sb_plan* pl, int n, int rows, int reps, int radix64, float* ms_per_launch) {
+    if (!pl || rows <= 0 || reps <= 0 || !ms_per_launch) return fail("sb_debug_fft_bench: bad arguments");
+    if (!is_pow2(n) || n < kMinFft || n > kMaxFftSupported) return fail("sb_debug_fft_bench: unsupported length");
+    const size_t bytes = (size_t)rows * n * sizeof(float2);
+    SB_OK(ensure(pl->raw, 2 * bytes));
+    float2* d_in = (float2*)pl->raw.p;
+    float2* d_out = d_in + (size_t)rows * n;
+    SB_TRY(sb_rt_memset(d_in, 0, bytes, pl->stream));
+    sb_event_t e0, e1;
+    sb_rt_event_create(&e0);
+    sb_rt_event_create(&e1);
+    int rc = 0;
+    for (int it = 0; it < reps + 1 && rc == 0; ++it) {
+        if (it == 1) sb_rt_event_record(e0, pl->stream);      // the first launch is the warm-up
+        if (radix64) {
+            if (n != sb64::N) { rc = fail("the radix-64 core is length 4096"); break; }
+            const float2* tw64 = nullptr;
+            rc = twiddles64(pl, &tw64);
+            if (rc) break;
+            constexpr size_t smem = (size_t)(4 * sb64::kXchg + sb64::kTwRows * sb64::R) * sizeof(float2);
+#ifndef SB_EMU
+            cudaFuncSetAttribute(sb64::k_fft4096_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+            SB_LAUNCH(sb64::k_fft4096_r64, dim3(div_up(rows, 4)), dim3(256), smem, pl->stream, rows, (const float2*)d_in,
+                      d_out, 0, tw64);
+            rc = check_launch(pl, "k_fft4096_r64");
+        } else {
+            const float2* tw = nullptr;
+            rc = twiddles<float>(pl, n, &tw);
+            if (rc) break;
+            rc = dispatch_n(n, [&](auto nn) {
+                constexpr int N = decltype(nn)::value;
+                using S = Shape<N, float>;
+                auto kern = sb::k_fft_rows<N, float>;
+                SB_ALLOW_SMEM(kern, S::smem);
+                SB_LAUNCH(kern, dim3(div_up(rows, S::GP)), dim3(S::threads), S::smem, pl->stream, rows,
+                          (const float2*)d_in, d_out, 0, tw);
+                return check_launch(pl, "k_fft_rows");
+            });
+        }
+    }
+    sb_rt_event_record(e1, pl->stream);
+    sb_rt_sync(pl->stream);
+    *ms_per_launch = sb_rt_event_ms(e0, e1) / (float)reps;
+    sb_rt_event_destroy(e0);
+    sb_rt_event_destroy(e1);
+    return rc;
 }
 
 int sb_sync(sb_plan* pl) {

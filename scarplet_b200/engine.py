@@ -395,10 +395,17 @@ class Plan(object):
         check(self.lib, self.lib.sb_fill_nodata(self._h, z.ctypes.data, float(max_search_distance), byref(left)))
         return int(left.value)
 
-    def debug_fft(self, x, inverse=False):
+    def debug_fft_bench(self, n, rows, reps=10, radix64=False):
+        """Developer hook: ms per launch of the batched FFT kernel alone."""
+        ms = ctypes.c_float()
+        check(self.lib, self.lib.sb_debug_fft_bench(self._h, int(n), int(rows), int(reps), int(bool(radix64)), byref(ms)))
+        return float(ms.value)
+
+    def debug_fft(self, x, inverse=False, radix64=False):
+        """Unit-test hook: batched complex64 FFT over rows (``radix64``: the 64 x 64 core)."""
         x = np.ascontiguousarray(x, dtype=np.complex64)
         rows, n = x.shape
         out = np.empty_like(x)
         check(self.lib, self.lib.sb_debug_fft(self._h, n, rows, x.ctypes.data, out.ctypes.data,
-                                              int(bool(inverse))))
+                                              int(bool(inverse)) | (2 if radix64 else 0)))
         return out

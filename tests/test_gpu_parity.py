@@ -40,6 +40,12 @@ def test_fft_core(cuda_lib, n):
     refi = np.fft.ifft(x.astype(np.complex128), axis=1) * n
     assert np.abs(y - ref).max() / np.abs(ref).max() < 5e-7
     assert np.abs(yi - refi).max() / np.abs(refi).max() < 5e-7
+    if n == 4096:            # the 64 x 64 core (sb_r64.cuh)
+        with Plan(16, 16, 1.0, 1.0) as plan:
+            y = plan.debug_fft(x, radix64=True)
+            yi = plan.debug_fft(x, inverse=True, radix64=True)
+        assert np.abs(y - ref).max() / np.abs(ref).max() < 5e-7
+        assert np.abs(yi - refi).max() / np.abs(refi).max() < 5e-7
 
 
 def test_laplacian_goldens_bit_exact(cuda_lib, golden):
