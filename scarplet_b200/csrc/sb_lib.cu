@@ -100,6 +100,7 @@ struct sb_plan {
     // four templates -- with fewer, half of its thread groups idle and the per-angle staging of
     // the spectrum columns is not amortised (C2: 94 ms persistent, 69 ms per-template)
     int conv_persist = -1;
+    int conv_r64 = 1;              // Py = 4096: column kernel on the radix-64 core (sb_r64.cuh)
     long launches = 0;
     double c2_scale = 1.0;
     double curv_sumsq = 0.0, curv_count = 0.0;   // over the plan's own rows (slab_lo .. slab_hi)
@@ -739,8 +740,28 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                 // every template column has at most two non-zero inputs per thread
                                 const bool sparse = hi_y <= S::T - 1 && lo_y >= -S::T;
                                 ProfScope prof(pl, K_CONV_COLS);
+                                const bool persist = pl->conv_persist > 0 || (pl->conv_persist < 0 && max_per_angle >= 4);
+                                if constexpr (N == sb64::N) {
+                                    if (pl->conv_r64 && persist && cnt <= sb64::kConvRMaxBatch) {
+                                        const float2* tw64 = nullptr;
+                                        SB_OK(twiddles64(pl, &tw64));
+                                        if (hi_y <= 3 * sb64::R - 1 && lo_y >= -3 * sb64::R) {
+                                            auto kern = sb64::k_conv_cols_r<true>;
+                                            SB_ALLOW_SMEM(kern, sb64::kConvRSmem);
+                                            SB_LAUNCH(kern, dim3(KX), dim3(sb64::kConvRThreads), sb64::kConvRSmem, pl->stream, g,
+                                                      d_tm, pb, cnt, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
+                                                      (float4*)pl->gbuf.p, tw64);
+                                        } else {
+                                            auto kern = sb64::k_conv_cols_r<false>;
+                                            SB_ALLOW_SMEM(kern, sb64::kConvRSmem);
+                                            SB_LAUNCH(kern, dim3(KX), dim3(sb64::kConvRThreads), sb64::kConvRSmem, pl->stream, g,
+                                                      d_tm, pb, cnt, a0, (const float4*)pl->trt.p, (const float2*)pl->fct.p,
+                                                      (float4*)pl->gbuf.p, tw64);
+                                        }
+                                        return check_launch(pl, "k_conv_cols_r");
+                                    }
+                                }
                                 if constexpr (N >= 1024 && N <= 4096) {
-                                    const bool persist = pl->conv_persist > 0 || (pl->conv_persist < 0 && max_per_angle >= 4);
                                     if (persist && cnt <= sb::kConvPMaxBatch) {
                                         constexpr size_t smem_p =
                                             (size_t)(sb::kConvPThreads / S::T) * 2 * sbfft::padded_len(N) * sizeof(float2) +
@@ -899,6 +920,7 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
         pl->own_stream = true;
     }
     if (const char* e = std::getenv("SB_CONV_P")) pl->conv_persist = std::atoi(e);
+    if (const char* e = std::getenv("SB_CONV_R64")) pl->conv_r64 = std::atoi(e);
 #ifdef SB_ABLATE
     if (const char* e = std::getenv("SB_DBG")) pl->dbg = std::atoi(e);
 #endif
@@ -951,6 +973,7 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
     if (k == "profile") { pl->profile = value != 0; return 0; }
     if (k == "fast") { pl->fast = value != 0; return 0; }
     if (k == "conv_persist") { pl->conv_persist = (int)value; return 0; }
+    if (k == "conv_r64") { pl->conv_r64 = value != 0; return 0; }
     if (k == "precision") {
         if (value != 32 && value != 64) return fail("precision must be 32 or 64");
         pl->precision = (int)value;

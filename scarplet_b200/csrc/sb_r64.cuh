@@ -17,7 +17,7 @@
 // its inputs digit-transposed and leaves natural order.  All indices are compile-time, so the
 // permutation costs nothing.
 #pragma once
-#include "sb_fft.cuh"
+#include "sb_kernels.cuh"
 
 namespace sb64 {
 
@@ -219,6 +219,162 @@ k_fft4096_r64(int rows, const float2* SB_RESTRICT in, float2* SB_RESTRICT outp, 
             const float2 v = x[slot(u)];
             outp[(long)r * N + t + R * u] = inverse ? make_float2(v.y, v.x) : v;
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// k_conv_cols_r<SPARSE>: the column kernel (core.py:359, 363: ft * fc, fm2 * fc2 and the
+// column half of ifft2) for Py = 4096 on the radix-64 core.  Persistent: grid (KX), a CTA owns
+// one spectrum column for the whole batch; 256 threads = 4 groups of 64 = 2 pairs.  A PAIR
+// takes one template at a time, its two groups transform the two fields (t * curv, M * curv^2)
+// side by side, each behind its own two-warp barrier:
+//
+//   template column (6 non-zero rows per thread when SPARSE) -> forward 4096 -> x curvature
+//   spectrum column (staged in shared memory once per run of same-angle templates) -> inverse
+//   4096 -> both fields of a row leave in one 16-byte store (gbuf layout of sb_kernels.cuh).
+//
+// For the combined store the groups swap halves through their (by then idle) exchange
+// buffers: group a keeps rows u < 32 and parks u >= 32, group b the other way round; one
+// pair-wide barrier; each group stores its half with the partner's values beside its own.
+// SPARSE: every template of the batch has |row offset| < 192, so a thread's non-zero inputs
+// are q = 0, 1, 2 and 61, 62, 63 (dft64_sparse6).
+// ---------------------------------------------------------------------------
+// rows u = 32 HALF .. 32 HALF + 31 of a finished column (row m = t + 64 u at slot(u)) into the
+// group's exchange buffer, for the partner group to pick up (register indices are static)
+template <int HALF>
+SB_DEVICE void park_half(const float2 (&x)[R], int t, float2* xch) {
+#pragma unroll
+    for (int u = 0; u < R / 2; ++u) xch[(u + HALF * (R / 2)) * R + t] = x[slot(u + HALF * (R / 2))];
+}
+// store rows u = 32 HALF .. of both fields: mine from registers, the partner's from its buffer.
+// FIELD: which of the two fields is mine.  Swapped back (inverse via forward) on the way out.
+template <int HALF, int FIELD>
+SB_DEVICE void store_half(const float2 (&x)[R], int t, const float2* xch_partner, float4* dst, int kx, int kpitch,
+                          int dly, int out_ny) {
+#pragma unroll
+    for (int u = 0; u < R / 2; ++u) {
+        const int uu = u + HALF * (R / 2);
+        const float2 mine = x[slot(uu)];
+        const float2 other = xch_partner[uu * R + t];
+        const int m = t + R * uu;
+        const int io = (m + dly) & (N - 1);
+        const float2 a = FIELD == 0 ? mine : other, b = FIELD == 0 ? other : mine;
+        if (io < out_ny) sb_st_stream(dst + sb::gbuf_index(m, kx, kpitch), make_float4(a.y, a.x, b.y, b.x));
+    }
+}
+
+constexpr int kConvRThreads = 256;
+constexpr int kConvRMaxBatch = 64;
+constexpr size_t kConvRSmem = (size_t)(4 * kXchg + 2 * N + kTwRows * R) * sizeof(float2) + kConvRMaxBatch * 4 * sizeof(int);
+
+template <bool SPARSE>
+SB_GLOBAL SB_LAUNCH_BOUNDS(kConvRThreads, 1)
+k_conv_cols_r(sb::Geom g, const sb::Tmpl* SB_RESTRICT tmpls, int tmpl_base, int cnt, int angle_base,
+              const float4* SB_RESTRICT trt, const float2* SB_RESTRICT fct, float4* SB_RESTRICT gbuf,
+              const float2* SB_RESTRICT tw64) {
+    const int grp = sb_tid() / R, t = sb_tid() % R;
+    const int pair = grp >> 1, f = grp & 1;                // field of this group: 0 = t * curv, 1 = M * curv^2
+    const int KX = g.Px / 2 + 1;
+    const int kx = sb_bx();
+    float2* sm = (float2*)sb_shared();
+    float2* xch = sm + grp * kXchg;                        // this group's exchange buffer
+    float2* xch_partner = sm + (grp ^ 1) * kXchg;
+    float2* spec_s = sm + 4 * kXchg;                       // [2][N]
+    float2* tw_s = spec_s + 2 * N;                         // [kTwRows][R]
+    int* s_meta = (int*)(tw_s + kTwRows * R);              // [kConvRMaxBatch][4]: sy_lo, sy_hi, angle
+    for (int i = sb_tid(); i < kTwRows * R; i += kConvRThreads) tw_s[i] = tw64[i];
+    for (int i = sb_tid(); i < cnt; i += kConvRThreads) {
+        const sb::Tmpl* p = tmpls + tmpl_base + i;
+        s_meta[4 * i + 0] = p->sy_lo;
+        s_meta[4 * i + 1] = p->sy_hi;
+        s_meta[4 * i + 2] = p->angle_id - angle_base;
+    }
+    const GroupBar gbar{1 + grp};
+    const int pbar = 5 + pair;
+    const float2* spec = spec_s + f * N + t;
+    sb_sync();
+
+    int s0 = 0;
+#pragma unroll 1
+    while (s0 < cnt) {
+        const int a_loc = s_meta[4 * s0 + 2];
+        int s1 = s0 + 1;
+        while (s1 < cnt && s_meta[4 * s1 + 2] == a_loc) ++s1;
+        if (s0 > 0) sb_sync();                              // the previous run's products are done
+        {
+            const float4* src = (const float4*)(fct + (((long)a_loc * 2) * KX + kx) * N);
+            const float4* src2 = (const float4*)(fct + (((long)a_loc * 2 + 1) * KX + kx) * N);
+            float4* dst = (float4*)spec_s;
+            for (int i = sb_tid(); i < N / 2; i += kConvRThreads) {
+                dst[i] = sb_ld_stream(src + i);
+                dst[N / 2 + i] = sb_ld_stream(src2 + i);
+            }
+        }
+        sb_sync();
+        // SPARSE: rows t, t + 64, t + 128 and t - 192, t - 128, t - 64 of the template column,
+        // fetched one template ahead so that their latency hides behind the transforms
+        float2 in[6];
+        auto fetch_sparse = [&](int p_loc) {
+            const int sy_lo = s_meta[4 * p_loc + 0], sy_hi = s_meta[4 * p_loc + 1];
+            const float2* src = (const float2*)(trt + ((long)p_loc * KX + kx) * g.syp) + f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int srow = j < 3 ? t + R * j : t + R * (j - 6);
+                in[j] = make_float2(0.f, 0.f);
+                if (srow >= sy_lo && srow <= sy_hi) in[j] = sb_ld_stream(src + 2 * (srow - sy_lo));
+            }
+        };
+        if (SPARSE && s0 + pair < s1) fetch_sparse(s0 + pair);
+#pragma unroll 1
+        for (int p_loc = s0 + pair; p_loc < s1; p_loc += 2) {
+            float2 x[R];
+            if (SPARSE) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) x[q] = make_float2(0.f, 0.f);
+                x[0] = in[0]; x[1] = in[1]; x[2] = in[2];
+                x[61] = in[3]; x[62] = in[4]; x[63] = in[5];
+                if (p_loc + 2 < s1) fetch_sparse(p_loc + 2);
+                dft64_sparse6(x);
+            } else {
+                const int sy_lo = s_meta[4 * p_loc + 0], sy_hi = s_meta[4 * p_loc + 1];
+                const float2* src = (const float2*)(trt + ((long)p_loc * KX + kx) * g.syp) + f;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int qy = t + R * q;
+                    const int srow = qy < N / 2 ? qy : qy - N;
+                    x[q] = make_float2(0.f, 0.f);
+                    if (srow >= sy_lo && srow <= sy_hi) x[q] = sb_ld_stream(src + 2 * (srow - sy_lo));
+                }
+                dft64<false>(x);
+            }
+            // forward: twiddles, transpose, second pass (logical u at slot(u))
+            twiddle64<true>(x, t, tw_s);
+            sb_bar(pbar, 2 * R);                            // the partner has read what I parked for the last template
+            exchange64<true>(x, t, xch, gbar);
+            dft64<false>(x);
+            // spectrum product (core.py:359 / :363); swap: inverse via forward
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const float2 pr = sbfft::cmul(x[slot(u)], spec[R * u]);
+                x[slot(u)] = make_float2(pr.y, pr.x);
+            }
+            // inverse: digit-transposed in, natural out; twiddles; transpose; last pass
+            dft64<true>(x);
+            twiddle64<false>(x, t, tw_s);
+            exchange64<false>(x, t, xch, gbar);
+            dft64<false>(x);                                // row m = t + 64 u at slot(u)
+            // swap halves with the partner group and store both fields of a row together
+            gbar();                                         // my group is done reading my exchange buffer
+            if (f == 0) park_half<1>(x, t, xch); else park_half<0>(x, t, xch);
+            sb_bar(pbar, 2 * R);
+            float4* dst = gbuf + (long)p_loc * N * g.kpitch;
+            if (f == 0) store_half<0, 0>(x, t, xch_partner, dst, kx, g.kpitch, g.dly, g.out_ny);
+            else store_half<1, 1>(x, t, xch_partner, dst, kx, g.kpitch, g.dly, g.out_ny);
+        }
+        // a pair that ran out of templates must still meet its partner's barriers: none are
+        // pending here, because both groups of a pair walk the same templates
+        s0 = s1;
     }
 }
 

@@ -183,6 +183,40 @@ def test_persistent_column_kernel(emu_lib, scale, ages):
     assert rep["snr_rel_p50"] < 1e-5 and rep["snr_rel_max_strong"] <= 1e-4, rep
 
 
+@pytest.mark.parametrize("scale,ages", [(10, [2.0, 20.0, 60.0, 150.0, 300.0]), (200, [5.0, 9.0, 14.0, 20.0])])
+def test_radix64_column_kernel(emu_lib, scale, ages):
+    """Column FFT length 4096 takes k_conv_cols_r (radix-64 core: 64 threads per transform, one
+    exchange; the two fields of a template side by side in a pair of groups, halves swapped
+    through the idle exchange buffers for the combined store): sparse (6 non-zero rows per
+    thread) and dense template columns, runs longer and shorter than the pair count --
+    against the radix-16 persistent kernel and the oracle."""
+    from scarplet_b200 import params as P
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.synth import synthetic_dem
+    from scarplet_b200.templates import Scarp
+    ny, nx = 4096, 96
+    z = synthetic_dem(ny, seed=23, nx=nx)
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)[[3, 90, 140]]
+    outs = {}
+    for r64 in (1, 0):
+        with Plan(ny, nx, 1.0, 1.0) as plan:
+            plan.set_option("conv_r64", r64)
+            plan.set_option("conv_persist", 1)
+            plan.set_dem(z)
+            a, t, age_of, angle_of = plan.build_sweep(Scarp._sb_spec, scale, ages, angles)
+            plan.reset()
+            plan.sweep(a, t)
+            outs[r64] = plan.finalize(age_of, angle_of)
+            assert plan.last_geometry()["Py"] == 4096
+    rep = stack_report(outs[1], outs[0])
+    assert rep["mask_equal"] and rep["index_agreement"] >= 0.9995 and rep["snr_rel_max_strong"] < 1e-4, rep
+    ref = O.compare((O.match_template(z, 1.0, 1.0, O.SCARP, scale, age, ang)
+                     for age in ages for ang in angles), ny, nx)
+    rep = stack_report(outs[1], np.stack(ref))
+    assert rep["mask_mismatch_unexplained"] == 0 and rep["index_agreement"] >= 0.999, rep
+    assert rep["snr_rel_max_strong"] <= 1e-4 and rep["amp_rel_max_strong"] <= 1e-4, rep
+
+
 @pytest.mark.parametrize("shape,angle", [((128, 128), 0.3), ((90, 140), -0.8)])
 def test_plugin_template_generic_path(emu_lib, shape, angle):
     """A template class the library has no generator for (tests/plugin_templates.py) goes
