@@ -403,17 +403,43 @@ struct FitPairCtx {
     int giA, giB;                     // raster rows of the two streams
     bool actA, actB;
     int ox, m0, out_nx, nx;
+    float* best_snr;
     float* best_amp;
     int* best_idx;
     const int4* cross;                // get_err_mask column ranges per (angle, raster row), or null
     int ny;
     int dbg;
-    float (&bsA)[E];
-    float (&bsB)[E];
+    // Running best SNR of the thread's 2 x 16 pixels as a FILTER: bfloat16 truncations (lower
+    // bounds) of the exact values, two per register (pixel q in the low half, q + 8 in the high
+    // half).  The exact values live in the best state in global memory: a pixel that passes the
+    // filter (rare after the first templates of a sweep) is checked against them there.  Sixteen
+    // registers instead of thirty-two keep the arrays out of local memory.
+    unsigned (&bpA)[E / 2];
+    unsigned (&bpB)[E / 2];
     float2 (&vb_in)[E];               // stream b's input, filled together with stream a's
-    unsigned chg;                     // bit q (+16 for row B): the pixel's best SNR changed
 
-    SB_DEVICE FitPairCtx(float (&a)[E], float (&b)[E], float2 (&vb)[E]) : bsA(a), bsB(b), vb_in(vb), chg(0u) {}
+    SB_DEVICE FitPairCtx(unsigned (&a)[E / 2], unsigned (&b)[E / 2], float2 (&vb)[E]) : bpA(a), bpB(b), vb_in(vb) {}
+
+    SB_DEVICE static float bound_lo(unsigned w) { return sb_bits_float(w << 16); }
+    SB_DEVICE static float bound_hi(unsigned w) { return sb_bits_float(w & 0xFFFF0000u); }
+    // pack the bfloat16 truncation of a non-negative float into the low / high half
+    SB_DEVICE static unsigned with_lo(unsigned w, float v) { return (w & 0xFFFF0000u) | (sb_float_bits(v) >> 16); }
+    SB_DEVICE static unsigned with_hi(unsigned w, float v) { return (w & 0x0000FFFFu) | (sb_float_bits(v) & 0xFFFF0000u); }
+
+    // pixel q of row gi passed the filter with SNR `snr`: first maximum wins (core.py:230-240);
+    // equal positive SNRs (in float32 mostly the -90 / +90 degree pair) go to the lower flat
+    // index, whatever the batch order.  Returns true when the pixel improved.
+    SB_DEVICE bool improve(int gi, int q, float snr, float amp, const FitT& k) {
+        const long o = (long)gi * nx + ox + ((m0 + q * T) & (N - 1));
+        const float cur = best_snr[o];
+        if (snr > cur || (snr == cur && k.idx < best_idx[o])) {
+            best_snr[o] = snr;
+            best_amp[o] = amp;
+            best_idx[o] = k.idx;
+            return true;
+        }
+        return false;
+    }
 
     SB_DEVICE void bar() const { sb_sync(); }
 
@@ -441,28 +467,18 @@ struct FitPairCtx {
         return direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
     }
 
-    template <int F> SB_DEVICE void epilogue(const float2 (&v)[E], float (&bs)[E]) {
+    template <int F> SB_DEVICE void epilogue(const float2 (&v)[E], unsigned (&bp)[E / 2]) {
         const int gi = F == 0 ? giA : giB;
         const FitT k = s_fit[slot];
         const unsigned mk = mask(k, gi, F == 0 ? actA : actB);
-        float* pa = best_amp + ((long)gi * nx + ox);
-        int* pi = best_idx + ((long)gi * nx + ox);
+        if (mk == 0u) return;                                  // the whole row is edge-masked
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             float amp, snr;
             fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
-            snr = ((mk >> q) & 1u) ? snr : -1.f;              // edge-masked: never wins
-            // first maximum wins (core.py:230-240); equal positive SNRs (in float32 mostly the
-            // -90 / +90 degree pair) go to the lower flat index, whatever the batch order.
-            // (A branch-free select over the 16 pixels was measured 3 % slower: it spills.)
-            if (snr >= bs[q] && snr > 0.f) {
-                const int jo = (m0 + q * T) & (N - 1);
-                if (snr > bs[q] || k.idx < pi[jo]) {
-                    bs[q] = snr;
-                    pa[jo] = amp;
-                    pi[jo] = k.idx;
-                    chg |= 1u << (q + 16 * F);
-                }
+            const float bound = q < 8 ? bound_lo(bp[q & 7]) : bound_hi(bp[q & 7]);
+            if (snr >= bound && snr > 0.f && ((mk >> q) & 1u)) {
+                if (improve(gi, q, snr, amp, k)) bp[q & 7] = q < 8 ? with_lo(bp[q & 7], snr) : with_hi(bp[q & 7], snr);
             }
         }
     }
@@ -472,17 +488,15 @@ struct FitPairCtx {
     // The window mask is applied to the candidate bits, not to the 16 values; improvements
     // (rare after the first templates of a sweep) are resolved after the common path.
     static constexpr bool SOA = K > 1;
-    template <int F> SB_DEVICE void epilogue2(const sbfft::pk_t (&re)[8], const sbfft::pk_t (&im)[8], float (&bs)[E]) {
+    template <int F> SB_DEVICE void epilogue2(const sbfft::pk_t (&re)[8], const sbfft::pk_t (&im)[8], unsigned (&bp)[E / 2]) {
         using namespace sbfft;
         const int gi = F == 0 ? giA : giB;
         const FitT k = s_fit[slot];
         const unsigned mk = mask(k, gi, F == 0 ? actA : actB);
-        float2 snr2[8], amp2[8];
-        unsigned cand = 0u;
+        if (mk == 0u) return;                                                  // the whole row is edge-masked
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const pk_t X = im[j], Tp = re[j];
-            amp2[j] = unpk(mul2(X, pk(k.amp_k, k.amp_k)));                    // core.py:360
             const pk_t pp = mul2(X, X);
             const float2 ppf = unpk(pp);
             const pk_t npp = pk(-ppf.x, -ppf.y);
@@ -494,30 +508,12 @@ struct FitPairCtx {
             const float2 err = unpk(fma2(num, pk(k.inv_n, k.inv_n), pk(k.eps_k, k.eps_k)));   // core.py:366
             const float s_lo = fabsf(sb_fdiv_fast(t1.x, err.x));               // core.py:367
             const float s_hi = fabsf(sb_fdiv_fast(t1.y, err.y));
-            snr2[j] = make_float2(s_lo, s_hi);
             // (a NaN SNR -- NaN in the DEM -- never wins here; k_poison_windows marks those pixels)
-            cand |= (s_lo >= bs[j] && s_lo > 0.f) ? (1u << j) : 0u;
-            cand |= (s_hi >= bs[j + 8] && s_hi > 0.f) ? (1u << (j + 8)) : 0u;
-        }
-        cand &= mk;                                                            // edge-masked: never wins
-        if (cand != 0u) {
-            float* pa = best_amp + ((long)gi * nx + ox);
-            int* pi = best_idx + ((long)gi * nx + ox);
-            // first maximum wins (core.py:230-240); equal positive SNRs (in float32 mostly the
-            // -90 / +90 degree pair) go to the lower flat index, whatever the batch order
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                if ((cand >> q) & 1u) {
-                    const float snr = q < 8 ? snr2[q & 7].x : snr2[q & 7].y;
-                    const float amp = q < 8 ? amp2[q & 7].x : amp2[q & 7].y;
-                    const int jo = (m0 + q * T) & (N - 1);
-                    if (snr > bs[q] || k.idx < pi[jo]) {
-                        bs[q] = snr;
-                        pa[jo] = amp;
-                        pi[jo] = k.idx;
-                        chg |= 1u << (q + 16 * F);
-                    }
-                }
+            if (s_lo >= bound_lo(bp[j]) && s_lo > 0.f && ((mk >> j) & 1u)) {
+                if (improve(gi, j, s_lo, unpk(X).x * k.amp_k, k)) bp[j] = with_lo(bp[j], s_lo);   // amp: core.py:360
+            }
+            if (s_hi >= bound_hi(bp[j]) && s_hi > 0.f && ((mk >> (j + 8)) & 1u)) {
+                if (improve(gi, j + 8, s_hi, unpk(X).y * k.amp_k, k)) bp[j] = with_hi(bp[j], s_hi);
             }
         }
     }
@@ -544,16 +540,16 @@ struct FitPairCtx {
             sbfft::pk_t re[8], im[8];
             sbfft::stage_math_soa<N, P>(v, w, re, im);
             if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
-            if constexpr (F == 0) epilogue2<0>(re, im, bsA);
-            else epilogue2<1>(re, im, bsB);
+            if constexpr (F == 0) epilogue2<0>(re, im, bpA);
+            else epilogue2<1>(re, im, bpB);
             return;
         }
 #endif
         sbfft::stage_math<N, P, float>(v, w);
         if constexpr (P == K - 1) {
             if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
-            if constexpr (F == 0) epilogue<0>(v, bsA);
-            else epilogue<1>(v, bsB);
+            if constexpr (F == 0) epilogue<0>(v, bpA);
+            else epilogue<1>(v, bpB);
         }
     }
     template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
@@ -617,9 +613,9 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
     sb_sync();
     const int n_act = s_list[2 * kFitMaxBatch];
 
-    float bsA[E], bsB[E];
+    unsigned bpA[E / 2], bpB[E / 2];
     float2 va[E], vb[E];
-    Ctx c(bsA, bsB, vb);
+    Ctx c(bpA, bpB, vb);
     c.t = t;
     c.smA = sm + (long)grp * 2 * PL;
     c.smB = c.smA + PL;
@@ -634,16 +630,26 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
     c.nx = g.nx;
     c.s_fit = s_fit;
     c.dbg = g.dbg;
+    c.best_snr = best_snr;
     c.best_amp = best_amp;
     c.best_idx = best_idx;
     c.cross = cross;
     c.ny = g.ny;
 #pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int jo = (t + q * T + g.dlx) & (N - 1);
-        const bool in = jo < g.out_nx;
-        bsA[q] = (actA && in) ? best_snr[(long)c.giA * g.nx + g.ox + jo] : 0.f;
-        bsB[q] = (actB && in) ? best_snr[(long)c.giB * g.nx + g.ox + jo] : 0.f;
+    for (int j = 0; j < E / 2; ++j) {
+        float lo[2], hi[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int jo = (t + (j + 8 * h) * T + g.dlx) & (N - 1);
+            const bool in = jo < g.out_nx;
+            const float a = (actA && in) ? best_snr[(long)c.giA * g.nx + g.ox + jo] : 0.f;
+            const float b = (actB && in) ? best_snr[(long)c.giB * g.nx + g.ox + jo] : 0.f;
+            // a NaN best (NaN in the DEM, k_poison_windows) stays: no SNR passes a NaN bound
+            (h == 0 ? lo : hi)[0] = a;
+            (h == 0 ? lo : hi)[1] = b;
+        }
+        bpA[j] = Ctx::with_hi(Ctx::with_lo(0u, lo[0]), hi[0]);
+        bpB[j] = Ctx::with_hi(Ctx::with_lo(0u, lo[1]), hi[1]);
     }
     const long row_off = gbuf_index(2 * pr, 0, g.kpitch);
     const long tmpl_pitch = (long)g.Py * g.kpitch;
@@ -664,12 +670,6 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
         // no barrier between templates: buffer A was last read before the final barrier,
         // buffer B is next written after the coming template's first barrier
         leapfrog<Ctx::K>(c, va, vb);
-    }
-#pragma unroll
-    for (int q = 0; q < E; ++q) {
-        const int jo = (t + q * T + g.dlx) & (N - 1);
-        if ((c.chg >> q) & 1u) best_snr[(long)c.giA * g.nx + g.ox + jo] = bsA[q];
-        if ((c.chg >> (q + 16)) & 1u) best_snr[(long)c.giB * g.nx + g.ox + jo] = bsB[q];
     }
 }
 

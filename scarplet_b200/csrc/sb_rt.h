@@ -165,6 +165,10 @@ inline float sb_rt_event_ms(sb_event_t a, sb_event_t b) { float ms = 0.f; cudaEv
 inline const char* sb_rt_error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 #endif
 
+// bit casts
+SB_DEVICE unsigned sb_float_bits(float v) { unsigned u; memcpy(&u, &v, 4); return u; }
+SB_DEVICE float sb_bits_float(unsigned u) { float v; memcpy(&v, &u, 4); return v; }
+
 // ---- precision-generic vector types ------------------------------------------
 template <typename R> struct Vec;
 template <> struct Vec<float> { typedef float2 v2; typedef float4 v4; };
