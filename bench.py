@@ -410,14 +410,17 @@ def run_ours(args):
         # ---- the same steps again with an event pair around every launch: per-kernel times --------
         plan.set_option("profile", 1)
         plan.profile(reset=True)
-        for _ in range(args.steps):
+        prof_steps = args.steps if args.profile_steps is None else args.profile_steps
+        for _ in range(prof_steps):
             step()
         fence()
         prof = plan.profile(reset=True)
         plan.set_option("profile", 0)
+        if prof_steps:
+            prof = {k: (v[0] * args.steps / prof_steps, v[1] * args.steps / prof_steps) for k, v in prof.items()}
         merge = float(np.mean([a.elapsed_time(b) for a, b in merge_ms])) if merge_ms else 0.0
 
-        stats = torch.tensor([ms_total, merge, float(plan.device_bytes + torch.cuda.max_memory_allocated(device))],
+        stats = torch.tensor([ms_total, merge, float(plan.device_bytes + torch.cuda.max_memory_allocated(device)), -merge],
                              dtype=torch.float64, device=device)
         n_launch = torch.tensor([launches], dtype=torch.int64, device=device)
         if world > 1:
@@ -526,6 +529,9 @@ def run_ours(args):
                           "lsu_wavefront_pct": c.get("lsu_wavefront_pct"), "fp32_pipe_pct": c.get("fma_pipe_pct"),
                           "issue_active_pct": c.get("issue_active_pct"), "counters_source": c.get("source")})
         per_kernel[k] = entry
+    if not per_kernel:
+        per_kernel = {"k_conv_cols": {"ms_per_step": 0.0, "algorithmic_GBps": None, "algorithmic_frac": None, "share_of_step": None}}
+        prof = {"k_conv_cols": (0.0, 0)}
     heavy = {k: v for k, v in per_kernel.items() if k in ("k_conv_cols", "k_fit_rows")}
     dom = max(heavy, key=lambda k: heavy[k]["ms_per_step"]) if heavy else max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     d = per_kernel[dom]
@@ -569,7 +575,11 @@ def run_ours(args):
                 "batches": [geo["angle_batch"], geo["template_batch"]]}),
             "clocks": clocks, "e2e": e2e, "e2e_dropin": dropin,
             "gpu_launches": int(n_launch.item()),
-            "merge_ms_per_step": float(stats[1].item()), "device_gb_per_rank_max": float(stats[2].item()) / 1e9,
+            # on the stream between the end of a rank's sweep and the end of its merge: the minimum over
+            # ranks is the exchange itself (the last rank to arrive waits for nobody), the maximum adds the
+            # wait of the first rank for the last (load imbalance)
+            "merge_ms_per_step": {"min_over_ranks": -float(stats[3].item()), "max_over_ranks": float(stats[1].item())},
+            "device_gb_per_rank_max": float(stats[2].item()) / 1e9,
             "host_wall_ms_per_step": wall_ms,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
@@ -594,6 +604,7 @@ def main():
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--ages", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--profile-steps", type=int, default=None, help="steps of the per-kernel timing pass (default: --steps; 0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
     ap.add_argument("--fast", type=int, default=None, help="developer switch: 0 = simple kernels")

@@ -403,43 +403,17 @@ struct FitPairCtx {
     int giA, giB;                     // raster rows of the two streams
     bool actA, actB;
     int ox, m0, out_nx, nx;
-    float* best_snr;
     float* best_amp;
     int* best_idx;
     const int4* cross;                // get_err_mask column ranges per (angle, raster row), or null
     int ny;
     int dbg;
-    // Running best SNR of the thread's 2 x 16 pixels as a FILTER: bfloat16 truncations (lower
-    // bounds) of the exact values, two per register (pixel q in the low half, q + 8 in the high
-    // half).  The exact values live in the best state in global memory: a pixel that passes the
-    // filter (rare after the first templates of a sweep) is checked against them there.  Sixteen
-    // registers instead of thirty-two keep the arrays out of local memory.
-    unsigned (&bpA)[E / 2];
-    unsigned (&bpB)[E / 2];
+    float (&bsA)[E];
+    float (&bsB)[E];
     float2 (&vb_in)[E];               // stream b's input, filled together with stream a's
+    unsigned chg;                     // bit q (+16 for row B): the pixel's best SNR changed
 
-    SB_DEVICE FitPairCtx(unsigned (&a)[E / 2], unsigned (&b)[E / 2], float2 (&vb)[E]) : bpA(a), bpB(b), vb_in(vb) {}
-
-    SB_DEVICE static float bound_lo(unsigned w) { return sb_bits_float(w << 16); }
-    SB_DEVICE static float bound_hi(unsigned w) { return sb_bits_float(w & 0xFFFF0000u); }
-    // pack the bfloat16 truncation of a non-negative float into the low / high half
-    SB_DEVICE static unsigned with_lo(unsigned w, float v) { return (w & 0xFFFF0000u) | (sb_float_bits(v) >> 16); }
-    SB_DEVICE static unsigned with_hi(unsigned w, float v) { return (w & 0x0000FFFFu) | (sb_float_bits(v) & 0xFFFF0000u); }
-
-    // pixel q of row gi passed the filter with SNR `snr`: first maximum wins (core.py:230-240);
-    // equal positive SNRs (in float32 mostly the -90 / +90 degree pair) go to the lower flat
-    // index, whatever the batch order.  Returns true when the pixel improved.
-    SB_DEVICE bool improve(int gi, int q, float snr, float amp, const FitT& k) {
-        const long o = (long)gi * nx + ox + ((m0 + q * T) & (N - 1));
-        const float cur = best_snr[o];
-        if (snr > cur || (snr == cur && k.idx < best_idx[o])) {
-            best_snr[o] = snr;
-            best_amp[o] = amp;
-            best_idx[o] = k.idx;
-            return true;
-        }
-        return false;
-    }
+    SB_DEVICE FitPairCtx(float (&a)[E], float (&b)[E], float2 (&vb)[E]) : bsA(a), bsB(b), vb_in(vb), chg(0u) {}
 
     SB_DEVICE void bar() const { sb_sync(); }
 
@@ -467,18 +441,28 @@ struct FitPairCtx {
         return direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
     }
 
-    template <int F> SB_DEVICE void epilogue(const float2 (&v)[E], unsigned (&bp)[E / 2]) {
+    template <int F> SB_DEVICE void epilogue(const float2 (&v)[E], float (&bs)[E]) {
         const int gi = F == 0 ? giA : giB;
         const FitT k = s_fit[slot];
         const unsigned mk = mask(k, gi, F == 0 ? actA : actB);
-        if (mk == 0u) return;                                  // the whole row is edge-masked
+        float* pa = best_amp + ((long)gi * nx + ox);
+        int* pi = best_idx + ((long)gi * nx + ox);
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             float amp, snr;
             fit_pixel_fast(v[q].y, v[q].x, k, amp, snr);
-            const float bound = q < 8 ? bound_lo(bp[q & 7]) : bound_hi(bp[q & 7]);
-            if (snr >= bound && snr > 0.f && ((mk >> q) & 1u)) {
-                if (improve(gi, q, snr, amp, k)) bp[q & 7] = q < 8 ? with_lo(bp[q & 7], snr) : with_hi(bp[q & 7], snr);
+            snr = ((mk >> q) & 1u) ? snr : -1.f;              // edge-masked: never wins
+            // first maximum wins (core.py:230-240); equal positive SNRs (in float32 mostly the
+            // -90 / +90 degree pair) go to the lower flat index, whatever the batch order.
+            // (A branch-free select over the 16 pixels was measured 3 % slower: it spills.)
+            if (snr >= bs[q] && snr > 0.f) {
+                const int jo = (m0 + q * T) & (N - 1);
+                if (snr > bs[q] || k.idx < pi[jo]) {
+                    bs[q] = snr;
+                    pa[jo] = amp;
+                    pi[jo] = k.idx;
+                    chg |= 1u << (q + 16 * F);
+                }
             }
         }
     }
@@ -488,15 +472,17 @@ struct FitPairCtx {
     // The window mask is applied to the candidate bits, not to the 16 values; improvements
     // (rare after the first templates of a sweep) are resolved after the common path.
     static constexpr bool SOA = K > 1;
-    template <int F> SB_DEVICE void epilogue2(const sbfft::pk_t (&re)[8], const sbfft::pk_t (&im)[8], unsigned (&bp)[E / 2]) {
+    template <int F> SB_DEVICE void epilogue2(const sbfft::pk_t (&re)[8], const sbfft::pk_t (&im)[8], float (&bs)[E]) {
         using namespace sbfft;
         const int gi = F == 0 ? giA : giB;
         const FitT k = s_fit[slot];
         const unsigned mk = mask(k, gi, F == 0 ? actA : actB);
-        if (mk == 0u) return;                                                  // the whole row is edge-masked
+        float2 snr2[8], amp2[8];
+        unsigned cand = 0u;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const pk_t X = im[j], Tp = re[j];
+            amp2[j] = unpk(mul2(X, pk(k.amp_k, k.amp_k)));                    // core.py:360
             const pk_t pp = mul2(X, X);
             const float2 ppf = unpk(pp);
             const pk_t npp = pk(-ppf.x, -ppf.y);
@@ -508,12 +494,30 @@ struct FitPairCtx {
             const float2 err = unpk(fma2(num, pk(k.inv_n, k.inv_n), pk(k.eps_k, k.eps_k)));   // core.py:366
             const float s_lo = fabsf(sb_fdiv_fast(t1.x, err.x));               // core.py:367
             const float s_hi = fabsf(sb_fdiv_fast(t1.y, err.y));
+            snr2[j] = make_float2(s_lo, s_hi);
             // (a NaN SNR -- NaN in the DEM -- never wins here; k_poison_windows marks those pixels)
-            if (s_lo >= bound_lo(bp[j]) && s_lo > 0.f && ((mk >> j) & 1u)) {
-                if (improve(gi, j, s_lo, unpk(X).x * k.amp_k, k)) bp[j] = with_lo(bp[j], s_lo);   // amp: core.py:360
-            }
-            if (s_hi >= bound_hi(bp[j]) && s_hi > 0.f && ((mk >> (j + 8)) & 1u)) {
-                if (improve(gi, j + 8, s_hi, unpk(X).y * k.amp_k, k)) bp[j] = with_hi(bp[j], s_hi);
+            cand |= (s_lo >= bs[j] && s_lo > 0.f) ? (1u << j) : 0u;
+            cand |= (s_hi >= bs[j + 8] && s_hi > 0.f) ? (1u << (j + 8)) : 0u;
+        }
+        cand &= mk;                                                            // edge-masked: never wins
+        if (cand != 0u) {
+            float* pa = best_amp + ((long)gi * nx + ox);
+            int* pi = best_idx + ((long)gi * nx + ox);
+            // first maximum wins (core.py:230-240); equal positive SNRs (in float32 mostly the
+            // -90 / +90 degree pair) go to the lower flat index, whatever the batch order
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                if ((cand >> q) & 1u) {
+                    const float snr = q < 8 ? snr2[q & 7].x : snr2[q & 7].y;
+                    const float amp = q < 8 ? amp2[q & 7].x : amp2[q & 7].y;
+                    const int jo = (m0 + q * T) & (N - 1);
+                    if (snr > bs[q] || k.idx < pi[jo]) {
+                        bs[q] = snr;
+                        pa[jo] = amp;
+                        pi[jo] = k.idx;
+                        chg |= 1u << (q + 16 * F);
+                    }
+                }
             }
         }
     }
@@ -540,16 +544,16 @@ struct FitPairCtx {
             sbfft::pk_t re[8], im[8];
             sbfft::stage_math_soa<N, P>(v, w, re, im);
             if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
-            if constexpr (F == 0) epilogue2<0>(re, im, bpA);
-            else epilogue2<1>(re, im, bpB);
+            if constexpr (F == 0) epilogue2<0>(re, im, bsA);
+            else epilogue2<1>(re, im, bsB);
             return;
         }
 #endif
         sbfft::stage_math<N, P, float>(v, w);
         if constexpr (P == K - 1) {
             if (SB_DBG_ON(dbg, 64) && v[0].x != 1.2345e-30f) return;
-            if constexpr (F == 0) epilogue<0>(v, bpA);
-            else epilogue<1>(v, bpB);
+            if constexpr (F == 0) epilogue<0>(v, bsA);
+            else epilogue<1>(v, bsB);
         }
     }
     template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
@@ -613,9 +617,9 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
     sb_sync();
     const int n_act = s_list[2 * kFitMaxBatch];
 
-    unsigned bpA[E / 2], bpB[E / 2];
+    float bsA[E], bsB[E];
     float2 va[E], vb[E];
-    Ctx c(bpA, bpB, vb);
+    Ctx c(bsA, bsB, vb);
     c.t = t;
     c.smA = sm + (long)grp * 2 * PL;
     c.smB = c.smA + PL;
@@ -630,26 +634,16 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
     c.nx = g.nx;
     c.s_fit = s_fit;
     c.dbg = g.dbg;
-    c.best_snr = best_snr;
     c.best_amp = best_amp;
     c.best_idx = best_idx;
     c.cross = cross;
     c.ny = g.ny;
 #pragma unroll
-    for (int j = 0; j < E / 2; ++j) {
-        float lo[2], hi[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int jo = (t + (j + 8 * h) * T + g.dlx) & (N - 1);
-            const bool in = jo < g.out_nx;
-            const float a = (actA && in) ? best_snr[(long)c.giA * g.nx + g.ox + jo] : 0.f;
-            const float b = (actB && in) ? best_snr[(long)c.giB * g.nx + g.ox + jo] : 0.f;
-            // a NaN best (NaN in the DEM, k_poison_windows) stays: no SNR passes a NaN bound
-            (h == 0 ? lo : hi)[0] = a;
-            (h == 0 ? lo : hi)[1] = b;
-        }
-        bpA[j] = Ctx::with_hi(Ctx::with_lo(0u, lo[0]), hi[0]);
-        bpB[j] = Ctx::with_hi(Ctx::with_lo(0u, lo[1]), hi[1]);
+    for (int q = 0; q < E; ++q) {
+        const int jo = (t + q * T + g.dlx) & (N - 1);
+        const bool in = jo < g.out_nx;
+        bsA[q] = (actA && in) ? best_snr[(long)c.giA * g.nx + g.ox + jo] : 0.f;
+        bsB[q] = (actB && in) ? best_snr[(long)c.giB * g.nx + g.ox + jo] : 0.f;
     }
     const long row_off = gbuf_index(2 * pr, 0, g.kpitch);
     const long tmpl_pitch = (long)g.Py * g.kpitch;
@@ -670,6 +664,12 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
         // no barrier between templates: buffer A was last read before the final barrier,
         // buffer B is next written after the coming template's first barrier
         leapfrog<Ctx::K>(c, va, vb);
+    }
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        const int jo = (t + q * T + g.dlx) & (N - 1);
+        if ((c.chg >> q) & 1u) best_snr[(long)c.giA * g.nx + g.ox + jo] = bsA[q];
+        if ((c.chg >> (q + 16)) & 1u) best_snr[(long)c.giB * g.nx + g.ox + jo] = bsB[q];
     }
 }
 
@@ -786,6 +786,154 @@ k_curv_rows_f(Geom g, const float4* SB_RESTRICT diffs, const Angle* SB_RESTRICT 
     split_from_shared<N>(c.smB, t, h1);
     if (2 * c.rp < c.need_rows)
         store_row_pair<N, float>(h0, h1, t, cr + (long)a_loc * KX * g.rpitch + 2 * c.rp, g.rpitch);
+}
+
+// ---------------------------------------------------------------------------
+// Curvature spectra without one 2-D transform per orientation.  The directional Laplacian is
+// linear in the three second differences (dem.py:103-104):
+//     curv(a)   = c2 dxx - sc dxy + s2 dyy                      (c2 = cos^2 a, sc = 2 sin a cos a, s2 = sin^2 a)
+//     curv(a)^2 = c2^2 dxx^2 + sc^2 dxy^2 + s2^2 dyy^2 - 2 c2 sc dxx dxy + 2 c2 s2 dxx dyy - 2 sc s2 dxy dyy
+// and so is the Fourier transform: the spectra of the NINE planes (3 differences, 6 products)
+// are computed once per FFT tile (five packed pairs through k_diff_rows_f / k_curv_cols) and
+// every orientation's F[curv], F[curv^2] are combinations of them with nine scalars --
+// k_combine_spectra, an elementwise pass at HBM speed -- instead of a row kernel and a column
+// kernel per orientation.  Plane order (pair pp, field f -> plane 2 pp + f):
+//   0 dxx   1 dxy   2 dyy   3 s dxx^2   4 s dxy^2   5 s dyy^2   6 s dxx dxy   7 s dxx dyy   8 s dxy dyy   9 unused
+// (s = c2_scale, the power of two that brings the quadratic planes to the magnitude of the
+// linear ones in the packed transforms).
+// ---------------------------------------------------------------------------
+constexpr int kDiffPairs = 5;
+constexpr int kDiffPlanes = 9;
+
+template <int N>
+struct DiffCtx {
+    static constexpr int K = sbfft::num_stages(N);
+    static constexpr int T = N / E;
+    int t;
+    float2 *smA, *smB;
+    const float2* tw;
+    const float4* diffs;               // [pixel][dxx, dxy, dyy, -] float32
+    int pp;                            // plane pair
+    int oy, ox, ny, nx, need_y_lo, need_x_lo, need_x_hi, split_x, poison;
+    int row0;
+    float c2_scale;
+    int rp;                            // row pair: rows 2 rp (stream a) and 2 rp + 1 (stream b)
+    int need_rows;
+
+    SB_DEVICE void bar() const { sb_sync(); }
+    template <int P> SB_DEVICE void twid(float2 (&w)[TW]) { sbfft::load_tw<N, P, float>(w, t, tw); }
+
+    SB_DEVICE float2 planes(const float4 d) const {
+        const float s = c2_scale;
+        switch (pp) {
+            case 0: return make_float2(d.x, d.y);
+            case 1: return make_float2(d.z, d.x * d.x * s);
+            case 2: return make_float2(d.y * d.y * s, d.z * d.z * s);
+            case 3: return make_float2(d.x * d.y * s, d.x * d.z * s);
+            default: return make_float2(d.y * d.z * s, 0.f);
+        }
+    }
+    template <int F> SB_DEVICE void fill(float2 (&v)[E]) const {
+        const int r = 2 * rp + F;
+        const bool active = r < need_rows;
+        int gi = wrap(oy + need_y_lo + (active ? r : 0), ny) - row0;
+        gi += gi < 0 ? ny : 0;                   // row of the slab
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const int qx = t + q * T;
+            const int sx = qx < split_x ? qx : qx - N;
+            float2 val = make_float2(0.f, 0.f);
+            if (active && sx >= need_x_lo && sx <= need_x_hi) {
+                const int gj = wrap_near(ox + sx, nx);
+                val = planes(sb_ldg(diffs + (long)gi * nx + gj));
+            }
+            // a NaN in the DEM reaches every output pixel (dem.py:105 through the reference's fft2)
+            if (poison && pp == 0 && r == 0 && qx == 0) val = make_float2(NAN, NAN);
+            v[q] = val;
+        }
+    }
+    template <int P, int F> SB_DEVICE void phase(float2 (&v)[E], const float2 (&w)[TW]) {
+        sbfft::stage_math<N, P, float>(v, w);
+    }
+    template <int P, int F> SB_DEVICE void store(const float2 (&v)[E]) {
+        sbfft::stage_store<N, P, float>(v, t, F == 0 ? smA : smB);
+    }
+    template <int F> SB_DEVICE void load(float2 (&v)[E]) { sbfft::stage_load<N, float>(v, t, F == 0 ? smA : smB); }
+};
+
+// grid (kDiffPairs, ceil(need_rows / 2 / GP)); output layout as k_curv_rows_f with the plane
+// pair in the place of the orientation: cr[pp][kx][rpitch rows] float4
+template <int N>
+SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
+k_diff_rows_f(Geom g, const float4* SB_RESTRICT diffs, float4* SB_RESTRICT cr, const float2* SB_RESTRICT tw) {
+    constexpr int T = N / E;
+    constexpr int GP = (T > 256 ? T : 256) / T;
+    constexpr int PL = sbfft::padded_len(N);
+    const int grp = sb_tid() / T, t = sb_tid() % T;
+    const int KX = N / 2 + 1;
+    DiffCtx<N> c;
+    c.t = t;
+    c.smA = (float2*)sb_shared() + (long)grp * 2 * PL;
+    c.smB = c.smA + PL;
+    c.tw = tw;
+    c.diffs = diffs;
+    c.pp = sb_bx();
+    c.oy = g.oy; c.ox = g.ox; c.ny = g.ny; c.nx = g.nx;
+    c.need_y_lo = g.need_y_lo; c.need_x_lo = g.need_x_lo; c.need_x_hi = g.need_x_hi;
+    c.split_x = g.split_x; c.poison = g.poison; c.c2_scale = (float)g.c2_scale;
+    c.row0 = g.row0;
+    c.rp = sb_by() * GP + grp;
+    c.need_rows = g.need_y_hi - g.need_y_lo + 1;
+    float2 va[E], vb[E];
+    c.template fill<0>(va);
+    c.template fill<1>(vb);
+    leapfrog<DiffCtx<N>::K>(c, va, vb);
+    sb_sync();                                  // every thread is done with the exchange buffers
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+        c.smA[sbfft::pad_index(t + q * T)] = va[q];
+        c.smB[sbfft::pad_index(t + q * T)] = vb[q];
+    }
+    sb_sync();
+    float4 h0[E / 2 + 1], h1[E / 2 + 1];
+    split_from_shared<N>(c.smA, t, h0);
+    split_from_shared<N>(c.smB, t, h1);
+    if (2 * c.rp < c.need_rows)
+        store_row_pair<N, float>(h0, h1, t, cr + (long)c.pp * KX * g.rpitch + 2 * c.rp, g.rpitch);
+}
+
+// per-orientation coefficients of the nine planes (host: float32 of the float64 cos / sin values)
+struct SpecCoef { float c[kDiffPlanes + 3]; };      // padded to 48 bytes
+
+// fct[a][field][kx][ky] = sum_p coef[a][p] * spec9[p][kx][ky] for the orientations a0 .. a0 + na - 1.
+// One thread per pair of adjacent ky (float4): nine 16-byte loads, then two 16-byte stores per
+// orientation.  n2 = planes' size in float4 units (KX * Py / 2).
+SB_GLOBAL k_combine_spectra(long n2, int na, int a0, const SpecCoef* SB_RESTRICT coef, const float4* SB_RESTRICT spec9,
+                            float4* SB_RESTRICT fct) {
+    SpecCoef* sc = (SpecCoef*)sb_shared();
+    for (int i = sb_tid(); i < na * (int)(sizeof(SpecCoef) / 4); i += 256) ((float*)sc)[i] = ((const float*)(coef + a0))[i];
+    sb_sync();
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n2) return;
+    float4 p[kDiffPlanes];
+#pragma unroll
+    for (int k = 0; k < kDiffPlanes; ++k) p[k] = sb_ld_stream(spec9 + (long)k * n2 + i);
+#pragma unroll 2
+    for (int a = 0; a < na; ++a) {
+        const SpecCoef& w = sc[a];
+        float4 A, B;
+        A.x = w.c[0] * p[0].x + w.c[1] * p[1].x + w.c[2] * p[2].x;
+        A.y = w.c[0] * p[0].y + w.c[1] * p[1].y + w.c[2] * p[2].y;
+        A.z = w.c[0] * p[0].z + w.c[1] * p[1].z + w.c[2] * p[2].z;
+        A.w = w.c[0] * p[0].w + w.c[1] * p[1].w + w.c[2] * p[2].w;
+        B.x = B.y = B.z = B.w = 0.f;
+#pragma unroll
+        for (int k = 3; k < kDiffPlanes; ++k) {
+            B.x += w.c[k] * p[k].x; B.y += w.c[k] * p[k].y; B.z += w.c[k] * p[k].z; B.w += w.c[k] * p[k].w;
+        }
+        sb_st_stream(fct + (long)(2 * a) * n2 + i, A);
+        sb_st_stream(fct + (long)(2 * a + 1) * n2 + i, B);
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -94,13 +94,16 @@ struct sb_plan {
     int* d_bidx = nullptr;
     std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
-    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux;
+    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux, spec9, coef;
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     // persistent column kernel: 1 always, 0 never, -1 (default) when a search angle carries at least
     // four templates -- with fewer, half of its thread groups idle and the per-angle staging of
     // the spectrum columns is not amortised (C2: 94 ms persistent, 69 ms per-template)
     int conv_persist = -1;
     int conv_r64 = 1;              // Py = 4096: column kernel on the radix-64 core (sb_r64.cuh)
+    // 1: the curvature spectra of an orientation are combinations of nine spectra computed once per
+    // FFT tile (k_diff_rows_f / k_combine_spectra); 0: one row + one column transform per orientation
+    int lincomb = 1;
     long launches = 0;
     double c2_scale = 1.0;
     double curv_sumsq = 0.0, curv_count = 0.0;   // over the plan's own rows (slab_lo .. slab_hi)
@@ -564,7 +567,23 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     }
 
     const int rpitch_max = need_rows_max + (need_rows_max & 1);
-    SB_OK(ensure(pl->cr, (size_t)Ba * KXm * rpitch_max * sizeof(C4)));
+    const bool lincomb = fast && pl->lincomb;
+    SB_OK(ensure(pl->cr, (size_t)std::max(Ba, lincomb ? sb::kDiffPairs : 0) * KXm * rpitch_max * sizeof(C4)));
+    if (lincomb) {
+        SB_OK(ensure(pl->spec9, (size_t)2 * sb::kDiffPairs * KXm * Pym * sizeof(float2)));
+        SB_OK(ensure(pl->coef, (size_t)n_angles * sizeof(sb::SpecCoef)));
+        std::vector<sb::SpecCoef> coef(n_angles);
+        for (int a = 0; a < n_angles; ++a) {
+            // the float32 values k_curv_rows_f uses: cos^2, 2 sin cos, sin^2 of the search angle
+            const double c2 = (double)(float)angles[a].cos2_a, sc = (double)(float)(2.0 * angles[a].sin_a * angles[a].cos_a),
+                         s2 = (double)(float)angles[a].sin2_a;
+            const double v[sb::kDiffPlanes] = {c2, -sc, s2, c2 * c2, sc * sc, s2 * s2, -2.0 * c2 * sc, 2.0 * c2 * s2, -2.0 * sc * s2};
+            for (int k = 0; k < sb::kDiffPlanes; ++k) coef[a].c[k] = (float)v[k];
+            for (int k = sb::kDiffPlanes; k < sb::kDiffPlanes + 3; ++k) coef[a].c[k] = 0.f;
+        }
+        SB_TRY(sb_rt_h2d(pl->coef.p, coef.data(), coef.size() * sizeof(sb::SpecCoef), pl->stream));
+        SB_TRY(sb_rt_sync(pl->stream));
+    }
     SB_OK(ensure(pl->fct, (size_t)Ba * 2 * KXm * Pym * sizeof(C2)));
     SB_OK(ensure(pl->trt, (size_t)Bt * KXm * syp * sizeof(C4)));
     SB_OK(ensure(pl->part, (size_t)Bt * syp * sizeof(double2)));
@@ -666,9 +685,40 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
             const int need_rows = g.need_y_hi - g.need_y_lo + 1;
             g.rpitch = need_rows + (need_rows & 1);
 
+            if (lincomb) {
+                // the nine plane spectra of this tile, once: five packed row transforms, column transforms
+                SB_OK(dispatch_n(Px, [&](auto nn) {
+                    constexpr int N = decltype(nn)::value;
+                    using S = Shape<N, float>;
+                    auto kern = sb::k_diff_rows_f<N>;
+                    SB_ALLOW_SMEM(kern, S::smem_conv_f);
+                    ProfScope prof(pl, K_CURV_ROWS);
+                    SB_LAUNCH(kern, dim3(sb::kDiffPairs, div_up(div_up(need_rows, 2), S::GP)), dim3(S::threads),
+                              S::smem_conv_f, pl->stream, g, (const float4*)pl->d_diffs32, (float4*)pl->cr.p,
+                              (const float2*)twx);
+                    return check_launch(pl, "k_diff_rows_f");
+                }));
+                SB_OK(dispatch_n(Py, [&](auto nn) {
+                    constexpr int N = decltype(nn)::value;
+                    using S = Shape<N, float>;
+                    auto kern = sb::k_curv_cols<N, float>;
+                    SB_ALLOW_SMEM(kern, S::smem);
+                    ProfScope prof(pl, K_CURV_ROWS);
+                    SB_LAUNCH(kern, dim3(div_up(KX, S::GP), sb::kDiffPairs), dim3(S::threads), S::smem,
+                              pl->stream, g, (const float4*)pl->cr.p, (float2*)pl->spec9.p, (const float2*)twy);
+                    return check_launch(pl, "k_curv_cols");
+                }));
+            }
             for (auto& ab : batches) {
                 const int a0 = ab.a0, a1 = ab.a1;
-                if (fast) {
+                if (lincomb) {
+                    const long n2 = (long)KX * Py / 2;
+                    ProfScope prof(pl, K_CURV_COLS);
+                    SB_LAUNCH(sb::k_combine_spectra, dim3(div_up(n2, 256)), dim3(256), (a1 - a0) * sizeof(sb::SpecCoef),
+                              pl->stream, n2, a1 - a0, a0, (const sb::SpecCoef*)pl->coef.p, (const float4*)pl->spec9.p,
+                              (float4*)pl->fct.p);
+                    SB_OK(check_launch(pl, "k_combine_spectra"));
+                } else if (fast) {
                     SB_OK(dispatch_n(Px, [&](auto nn) {
                         constexpr int N = decltype(nn)::value;
                         using S = Shape<N, float>;
@@ -691,6 +741,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                               S::smem, pl->stream, g, (const double*)pl->d_diffs, d_an, a0, (C4*)pl->cr.p, twx);
                     return check_launch(pl, "k_curv_rows");
                 }));
+                if (!lincomb)
                 SB_OK(dispatch_n(Py, [&](auto nn) {
                     constexpr int N = decltype(nn)::value;
                     using S = Shape<N, R>;
@@ -921,6 +972,7 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
     }
     if (const char* e = std::getenv("SB_CONV_P")) pl->conv_persist = std::atoi(e);
     if (const char* e = std::getenv("SB_CONV_R64")) pl->conv_r64 = std::atoi(e);
+    if (const char* e = std::getenv("SB_LINCOMB")) pl->lincomb = std::atoi(e);
 #ifdef SB_ABLATE
     if (const char* e = std::getenv("SB_DBG")) pl->dbg = std::atoi(e);
 #endif
@@ -949,7 +1001,7 @@ int sb_plan_destroy(sb_plan* pl) {
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
     for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
     for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux})
+                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef})
         release(*b);
 #ifndef SB_EMU
     if (pl->own_stream) cudaStreamDestroy(pl->stream);
@@ -974,6 +1026,7 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
     if (k == "fast") { pl->fast = value != 0; return 0; }
     if (k == "conv_persist") { pl->conv_persist = (int)value; return 0; }
     if (k == "conv_r64") { pl->conv_r64 = value != 0; return 0; }
+    if (k == "lincomb") { pl->lincomb = value != 0; return 0; }
     if (k == "precision") {
         if (value != 32 && value != 64) return fail("precision must be 32 or 64");
         pl->precision = (int)value;
@@ -1038,7 +1091,7 @@ long sb_plan_device_bytes(const sb_plan* pl) {
     if (pl->d_diffs32) b += n * sizeof(float4);
     b += (size_t)pl->bn() * pl->n_states * 12;
     for (const Buf* q : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux})
+                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef})
         b += q->cap;
     return (long)b;
 }
