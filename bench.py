@@ -360,11 +360,11 @@ def run_ours(args):
             plan.set_dem(z_pinned.numpy())                       # inputs resident in HBM
         if rows_mode:
             D.share_dem_stats(plan, device=device)
-            lo, hi = 0, len(angles)
+            a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, scale_arg, ages, angles, "age_major")
         else:
-            lo, hi = D.shard_bounds(len(angles), world, rank)
-        a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, scale_arg, ages, angles, "age_major",
-                                                         angle_slice=(lo, hi))
+            a_rec, t_rec, age_of, angle_of = plan.build_sweep(spec, scale_arg, ages, angles, "age_major",
+                                                             template_share=(rank, world))
+        my_templates = t_rec[1]
         merge_ms = []
 
         def step(timed=False):
@@ -504,7 +504,7 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    my_evals = int(n) * int(row_hi - row_lo) * len(ages) * (hi - lo) * len(scales) * args.steps   # rank 0's share
+    my_evals = int(n) * int(row_hi - row_lo) * my_templates * args.steps   # rank 0's share
     tpa = len(ages) * len(scales)
     batch = max(1, geo["template_batch"])
     counters = load_profile_counters()

@@ -157,10 +157,10 @@ struct ConvCtx {
 #endif
                     if (SB_DBG_ON(dbg, 1) && v[q].x != 1.2345e-30f) continue;
                     if (SB_DBG_ON(dbg, 128)) {      // timing only: same bytes, fully coalesced
-                        sb_st_stream(dst + ((long)kx * N + t + q * T), make_float4(a.y, a.x, v[q].y, v[q].x));
+                        sb_st_stream(dst + ((long)kx * N + t + q * T), gbuf_pack<float2, float4>(a, v[q]));
                         continue;
                     }
-                    if (io < out_ny) sb_st_stream(dst + gbuf_index(t + q * T, kx, kpitch), make_float4(a.y, a.x, v[q].y, v[q].x));
+                    if (io < out_ny) sb_st_stream(dst + gbuf_index(t + q * T, kx, kpitch), gbuf_pack<float2, float4>(a, v[q]));
                 }
             }
         }
@@ -436,9 +436,10 @@ struct FitPairCtx {
         return qlo <= qhi ? ((2u << qhi) - (1u << qlo)) : 0u;
     }
 
-    // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped (inverse via forward)
+    // X(k) = Gt(k) + i Gm(k) and X(N-k) = conj Gt(k) + i conj Gm(k) come ready (and swapped: inverse
+    // via forward) in the element (gbuf_pack)
     SB_DEVICE static float2 herm(const float4 g4, bool direct) {
-        return direct ? make_float2(g4.y + g4.z, g4.x - g4.w) : make_float2(g4.z - g4.y, g4.x + g4.w);
+        return direct ? make_float2(g4.x, g4.y) : make_float2(g4.z, g4.w);
     }
 
     template <int F> SB_DEVICE void epilogue(const float2 (&v)[E], float (&bs)[E]) {
@@ -566,7 +567,12 @@ template <int N>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
 k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RESTRICT fit,
              const float4* SB_RESTRICT gbuf, float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
-             const float2* SB_RESTRICT tw, const int4* SB_RESTRICT cross) {
+             const float2* SB_RESTRICT tw, const int4* SB_RESTRICT cross, float* sub_snr, float* sub_amp, int* sub_idx,
+             long sub_stride) {
+    // grid.y > 1 (small rasters, whose row pairs alone do not fill the GPU): the templates of the
+    // launch are dealt round-robin to grid.y sub-streams; sub-stream 0 folds into the best state
+    // itself, sub-stream j > 0 into its own copy (sub_* + (j - 1) * sub_stride), and k_best_fold
+    // merges the copies after the sweep.
     // `slots` (optional): the `count` batch slots this launch folds -- the templates of one best
     // state (template scale) inside a batch that mixes several; null: slots 0 .. count - 1.
     // best_*: the state's planes, offset so that raster row gi is at gi * nx (row slabs).
@@ -600,7 +606,7 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
         s_fit[sb_tid()] = k;
         s_gslot[sb_tid()] = slot;
         int flag = 0;
-        for (int r = 0; r < 2 * GP; ++r) {
+        for (int r = 0; r < 2 * GP && sb_tid() % sb_nby() == sb_by(); ++r) {
             const int m = 2 * sb_bx() * GP + r;
             const int io = (m + g.dly) & (g.Py - 1);
             if (m < g.Py && io < g.out_ny && g.oy + io >= k.i_lo && g.oy + io <= k.i_hi) flag = 1;
@@ -634,6 +640,11 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
     c.nx = g.nx;
     c.s_fit = s_fit;
     c.dbg = g.dbg;
+    if (sb_by() > 0) {
+        best_snr = sub_snr + (sb_by() - 1) * sub_stride;
+        best_amp = sub_amp + (sb_by() - 1) * sub_stride;
+        best_idx = sub_idx + (sb_by() - 1) * sub_stride;
+    }
     c.best_amp = best_amp;
     c.best_idx = best_idx;
     c.cross = cross;
@@ -918,18 +929,21 @@ SB_GLOBAL k_combine_spectra(long n2, int na, int a0, const SpecCoef* SB_RESTRICT
     float4 p[kDiffPlanes];
 #pragma unroll
     for (int k = 0; k < kDiffPlanes; ++k) p[k] = sb_ld_stream(spec9 + (long)k * n2 + i);
-#pragma unroll 2
+    // explicit fused multiply-adds in a fixed order: an orientation's spectra must not depend on
+    // its position in the batch (the sharded searches are bit-identical to the single-GPU one)
+#pragma unroll 1
     for (int a = 0; a < na; ++a) {
         const SpecCoef& w = sc[a];
         float4 A, B;
-        A.x = w.c[0] * p[0].x + w.c[1] * p[1].x + w.c[2] * p[2].x;
-        A.y = w.c[0] * p[0].y + w.c[1] * p[1].y + w.c[2] * p[2].y;
-        A.z = w.c[0] * p[0].z + w.c[1] * p[1].z + w.c[2] * p[2].z;
-        A.w = w.c[0] * p[0].w + w.c[1] * p[1].w + w.c[2] * p[2].w;
-        B.x = B.y = B.z = B.w = 0.f;
+        A.x = fmaf(w.c[2], p[2].x, fmaf(w.c[1], p[1].x, w.c[0] * p[0].x));
+        A.y = fmaf(w.c[2], p[2].y, fmaf(w.c[1], p[1].y, w.c[0] * p[0].y));
+        A.z = fmaf(w.c[2], p[2].z, fmaf(w.c[1], p[1].z, w.c[0] * p[0].z));
+        A.w = fmaf(w.c[2], p[2].w, fmaf(w.c[1], p[1].w, w.c[0] * p[0].w));
+        B.x = w.c[3] * p[3].x; B.y = w.c[3] * p[3].y; B.z = w.c[3] * p[3].z; B.w = w.c[3] * p[3].w;
 #pragma unroll
-        for (int k = 3; k < kDiffPlanes; ++k) {
-            B.x += w.c[k] * p[k].x; B.y += w.c[k] * p[k].y; B.z += w.c[k] * p[k].z; B.w += w.c[k] * p[k].w;
+        for (int k = 4; k < kDiffPlanes; ++k) {
+            B.x = fmaf(w.c[k], p[k].x, B.x); B.y = fmaf(w.c[k], p[k].y, B.y);
+            B.z = fmaf(w.c[k], p[k].z, B.z); B.w = fmaf(w.c[k], p[k].w, B.w);
         }
         sb_st_stream(fct + (long)(2 * a) * n2 + i, A);
         sb_st_stream(fct + (long)(2 * a + 1) * n2 + i, B);

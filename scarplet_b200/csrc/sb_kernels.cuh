@@ -102,8 +102,13 @@ struct FitT {
     int angle_id;            // row of the k_err_cross table
 };
 
-// gbuf (the inverse-column planes handed from the column kernel to the row kernel) holds,
-// per template, Py domain rows m of kpitch C4 elements, two rows interleaved:
+// gbuf (the inverse-column planes handed from the column kernel to the row kernel).  With Gt,
+// Gm the inverse-column transforms of ft * fc and fm2 * fc2 (core.py:359, 363), an element holds
+// the two inputs the inverse ROW transform of X = Gt + i Gm needs from it, ready to use:
+//     (Im X(k), Re X(k), Im X(N - k), Re X(N - k)),   X(N - k) = conj Gt(k) + i conj Gm(k)
+// (real and imaginary parts swapped: the inverse runs as a forward transform) -- the column
+// kernels have both fields in registers when they store, so the Hermitian extension costs the
+// row kernel no arithmetic.  Per template, Py domain rows m of kpitch C4 elements, two rows interleaved:
 // [m / 2][kx][m & 1].  The column kernel has rows m, m + 1 in adjacent lanes, so a warp
 // store fills whole 32-byte sectors (a 16-byte half-sector store runs at 0.9 TB/s on
 // B200, a full-sector one at 4.7 TB/s: scratch/ubench_scatter.cu); the row kernel reads
@@ -112,6 +117,17 @@ struct FitT {
 #define SB_GBUF_ROWS 2
 #endif
 constexpr int kGbufRows = SB_GBUF_ROWS;      // rows interleaved per spectrum column (power of two, even)
+// a, b: the two fields' inverse-column results as the transforms leave them (swapped: (im, re))
+template <typename C2, typename C4>
+SB_DEVICE C4 gbuf_pack(const C2 a, const C2 b) {
+    C4 r;
+    r.x = a.x + b.y;      // Im X(k)     = Im Gt + Re Gm
+    r.y = a.y - b.x;      // Re X(k)     = Re Gt - Im Gm
+    r.z = b.y - a.x;      // Im X(N - k) = Re Gm - Im Gt
+    r.w = a.y + b.x;      // Re X(N - k) = Re Gt + Im Gm
+    return r;
+}
+
 SB_DEVICE long gbuf_index(int m, int kx, int kpitch) {
     return ((long)(m / kGbufRows) * kpitch + kx) * kGbufRows + (m % kGbufRows);
 }
@@ -607,7 +623,7 @@ k_conv_cols(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int angle_base
                 const int m = t + q * T;
                 const int io = (m + g.dly) & (N - 1);
                 const C2 a = park[m];
-                if (io < g.out_ny) dst[gbuf_index(m, kx, g.kpitch)] = mk4<R>(a.y, a.x, v[q].y, v[q].x);
+                if (io < g.out_ny) dst[gbuf_index(m, kx, g.kpitch)] = gbuf_pack<C2, C4>(a, v[q]);
             }
         }
     }
@@ -701,9 +717,8 @@ k_fit_rows(Geom g, const Tmpl* SB_RESTRICT tmpls, int tmpl_base, int count, cons
             const int kk = direct ? k : N - k;
             C4 w = mk4<R>((R)0, (R)0, (R)0, (R)0);
             if (active) w = ld4(grow + kGbufRows * kk);
-            // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k); stored swapped
-            const C2 x = direct ? mk2<R>(w.x - w.w, w.y + w.z) : mk2<R>(w.x + w.w, w.z - w.y);
-            v[q] = mk2<R>(x.y, x.x);
+            // X(k) = Gt(k) + i Gm(k);  X(N-k) = conj Gt(k) + i conj Gm(k): both ready in the element (gbuf_pack)
+            v[q] = direct ? mk2<R>(w.x, w.y) : mk2<R>(w.z, w.w);
         }
         sbfft::forward<N, R>(v, t, sm, tw);
         const bool row_ok = gi >= p.i_lo && gi <= p.i_hi;
@@ -875,6 +890,24 @@ SB_GLOBAL k_best_merge(long n, int n_cands, const float* SB_RESTRICT snr_c, cons
         if (s != s || s > bs || (s == bs && k < bi)) { bs = s; ba = amp_c[(long)c * n + i]; bi = k; }
     }
     snr[i] = bs; amp[i] = ba; idx[i] = bi;
+}
+
+// Fold `n_extra` further copies of a best state (copy c of pixel i at [c * stride + i]) into the
+// main one in place, with k_best_merge's rule.
+SB_GLOBAL k_best_fold(long n, int n_extra, long stride, const float* SB_RESTRICT snr_x, const float* SB_RESTRICT amp_x,
+                      const int* SB_RESTRICT idx_x, float* SB_RESTRICT snr, float* SB_RESTRICT amp, int* SB_RESTRICT idx) {
+    const long i = (long)sb_bx() * 256 + sb_tid();
+    if (i >= n) return;
+    float bs = snr[i], ba = amp[i];
+    int bi = idx[i];
+    bool changed = false;
+    for (int c = 0; c < n_extra; ++c) {
+        if (bs != bs) break;
+        const float s = snr_x[(long)c * stride + i];
+        const int k = idx_x[(long)c * stride + i];
+        if (s != s || s > bs || (s == bs && k < bi)) { bs = s; ba = amp_x[(long)c * stride + i]; bi = k; changed = true; }
+    }
+    if (changed) { snr[i] = bs; amp[i] = ba; idx[i] = bi; }
 }
 
 // decode the best state into the reference's [amp, age, angle, snr] float64 planes

@@ -94,7 +94,8 @@ struct sb_plan {
     int* d_bidx = nullptr;
     std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
-    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux, spec9, coef;
+    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux, spec9, coef, subbest;
+    int fit_substreams = 0;        // 0: automatic (small rasters), else the number of sub-streams of the fit kernel
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     // persistent column kernel: 1 always, 0 never, -1 (default) when a search angle carries at least
     // four templates -- with fewer, half of its thread groups idle and the per-angle staging of
@@ -297,6 +298,8 @@ void apply_curv_stats(sb_plan* pl, double sumsq, double count) {
     pl->dem_nonfinite = !std::isfinite(sumsq);
 }
 
+long bn_all(const sb_plan* pl) { return pl->bn() * pl->n_states; }
+
 int alloc_best(sb_plan* pl) {
     for (void* p : {(void*)pl->d_bsnr, (void*)pl->d_bamp, (void*)pl->d_bidx})
         if (p) sb_rt_free(p);
@@ -349,14 +352,15 @@ int ensure_diffs64(sb_plan* pl) {
     return 0;
 }
 
-// relative cost per point of the kernels at FFT length P (4096 is the length they are tuned for;
-// 8192 needs a fourth exchange stage and has no persistent column kernel)
+// relative cost per point of the per-template kernels at FFT length P, measured (bench.py, one
+// B200): 4096 has the radix-64 column kernel; 8192 needs a fourth exchange stage and has no
+// persistent column kernel (C4 at 8192 periodic: 1.9 x the time per pixel of C3 at 4096)
 double length_weight(int P) {
     switch (P) {
-        case 8192: return 1.25;
+        case 8192: return 1.9;
         case 4096: return 1.0;
-        case 2048: return 1.05;
-        case 1024: return 1.12;
+        case 2048: return 1.1;
+        case 1024: return 1.15;
         default: return 1.3;
     }
 }
@@ -375,22 +379,28 @@ int plan_axis(const sb_plan* pl, int n, int r0, int r1, int lo, int hi, bool all
     const int len = r1 - r0;
     // complex128 at 8192 would need 270 KB of shared memory per column in k_conv_cols
     const int max_fft = std::min(pl->max_fft, pl->precision == 64 ? 4096 : kMaxFftSupported);
-    if (allow_periodic && r0 == 0 && r1 == n && is_pow2(n) && n >= kMinFft && n <= max_fft && !pl->force_pad) {
+    const bool can_periodic = allow_periodic && r0 == 0 && r1 == n && is_pow2(n) && n >= kMinFft && n <= max_fft &&
+                              !pl->force_pad;
+    auto take_periodic = [&]() {
         ax->periodic = true;
+        ax->tiles.clear();
         TileSpec t;
         t.P = n; t.o = 0; t.out = n;
         ax->tiles.push_back(t);
         return 0;
-    }
+    };
+    if (can_periodic && (!pl->mixed_tiles || n <= 4096)) return take_periodic();
     ax->periodic = false;
     std::vector<int> Ps;
     for (int P = kMinFft; P <= max_fft; P <<= 1) {
         if (P < ext + 1 || hi >= P / 2 || -lo > P / 2 || P - ext < 1) continue;
         Ps.push_back(P);
     }
-    if (Ps.empty())
+    if (Ps.empty()) {
+        if (can_periodic) return take_periodic();
         return fail("template support (" + std::to_string(ext) + " px) does not fit max_fft=" +
                     std::to_string(max_fft));
+    }
     std::vector<int> chosen;
     if (pl->mixed_tiles) {
         // covering knapsack: best[r] = least cost to cover r more pixels
@@ -405,6 +415,8 @@ int plan_axis(const sb_plan* pl, int n, int r0, int r1, int lo, int hi, bool all
                 if (best[r] < 0 || c < best[r] - 1e-9) { best[r] = c; pick[r] = P; }
             }
         }
+        // the exact circular domain of a power-of-two axis, when it is cheaper than padded tiles
+        if (can_periodic && n * length_weight(n) <= best[len]) return take_periodic();
         for (int r = len; r > 0; r = std::max(0, r - (pick[r] - ext))) chosen.push_back(pick[r]);
         std::sort(chosen.begin(), chosen.end(), [](int a, int b) { return a > b; });
     } else {
@@ -653,6 +665,28 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     // the host vectors must outlive the async copies
     SB_TRY(sb_rt_sync(pl->stream));
 
+    // Sub-streams of the fit kernel: a small raster has too few row pairs to fill 148 SMs, so the
+    // templates of a launch are dealt to nsub sub-streams (grid.y), each with its own copy of the
+    // best state; the copies are folded into the plan's state at the end of the sweep.
+    int nsub = 1;
+    if (fast && !so.raw_amp) {
+        nsub = pl->fit_substreams;
+        if (nsub == 0) {
+            const int T = std::max(Pxm / sbfft::E, 1), gp = std::max(256 / T, 1);
+            const int ctas = div_up(Pym / 2, gp);
+            nsub = std::max(1, std::min(8, 300 / std::max(ctas, 1)));
+        }
+        nsub = std::max(1, std::min(nsub, Bt / 2));
+    }
+    const long sub_stride = bn_all(pl);
+    if (nsub > 1) {
+        const size_t cnt_x = (size_t)(nsub - 1) * sub_stride;
+        SB_OK(ensure(pl->subbest, cnt_x * 12));
+        SB_LAUNCH(sb::k_best_init, dim3(div_up((long)cnt_x, 256)), dim3(256), 0, pl->stream, (long)cnt_x, (float*)pl->subbest.p,
+                  (float*)pl->subbest.p + cnt_x, (int*)((float*)pl->subbest.p + 2 * cnt_x));
+        SB_OK(check_launch(pl, "k_best_init"));
+    }
+
     pl->last_geom[0] = Pym; pl->last_geom[1] = Pxm; pl->last_geom[2] = (int)ay.tiles.size();
     pl->last_geom[3] = (int)ax.tiles.size(); pl->last_geom[4] = Ba; pl->last_geom[5] = Bt;
     pl->last_fft_area = 0.0;
@@ -879,10 +913,14 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                     ProfScope prof(pl, K_FIT_ROWS);
                                     auto kern = sb::k_fit_rows_g<N>;
                                     SB_ALLOW_SMEM(kern, S::smem_fit_f);
-                                    SB_LAUNCH(kern, dim3(div_up(Py / 2, S::GP)), dim3(S::threads), S::smem_fit_f,
+                                    const size_t cnt_x = (size_t)(nsub - 1) * sub_stride;
+                                    float* xs = nsub > 1 ? (float*)pl->subbest.p + (long)gp.state * bn - boff : nullptr;
+                                    SB_LAUNCH(kern, dim3(div_up(Py / 2, S::GP), nsub), dim3(S::threads), S::smem_fit_f,
                                               pl->stream, g, gp.count, d_slots, (const sb::FitT*)pl->fit.p,
                                               (const float4*)pl->gbuf.p, bsnr, bamp, bidx, (const float2*)twx,
-                                              gp.err ? (const int4*)pl->cross.p : (const int4*)nullptr);
+                                              gp.err ? (const int4*)pl->cross.p : (const int4*)nullptr, xs,
+                                              nsub > 1 ? xs + cnt_x : nullptr, nsub > 1 ? (int*)(xs + 2 * cnt_x) : nullptr,
+                                              sub_stride);
                                     return check_launch(pl, "k_fit_rows_g");
                                 }));
                                 if (g.poison) {
@@ -911,6 +949,13 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                 }
             }
         }
+    if (nsub > 1) {
+        const size_t cnt_x = (size_t)(nsub - 1) * sub_stride;
+        const float* xs = (const float*)pl->subbest.p;
+        SB_LAUNCH(sb::k_best_fold, dim3(div_up(sub_stride, 256)), dim3(256), 0, pl->stream, sub_stride, nsub - 1, sub_stride,
+                  xs, xs + cnt_x, (const int*)(xs + 2 * cnt_x), pl->d_bsnr, pl->d_bamp, pl->d_bidx);
+        SB_OK(check_launch(pl, "k_best_fold"));
+    }
     drain_profile(pl);
     return 0;
 }
@@ -1001,7 +1046,7 @@ int sb_plan_destroy(sb_plan* pl) {
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
     for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
     for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef})
+                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef, &pl->subbest})
         release(*b);
 #ifndef SB_EMU
     if (pl->own_stream) cudaStreamDestroy(pl->stream);
@@ -1027,6 +1072,7 @@ int sb_plan_set_option(sb_plan* pl, const char* key, long value) {
     if (k == "conv_persist") { pl->conv_persist = (int)value; return 0; }
     if (k == "conv_r64") { pl->conv_r64 = value != 0; return 0; }
     if (k == "lincomb") { pl->lincomb = value != 0; return 0; }
+    if (k == "fit_substreams") { pl->fit_substreams = (int)std::max(0L, std::min(8L, value)); return 0; }
     if (k == "precision") {
         if (value != 32 && value != 64) return fail("precision must be 32 or 64");
         pl->precision = (int)value;
@@ -1091,7 +1137,7 @@ long sb_plan_device_bytes(const sb_plan* pl) {
     if (pl->d_diffs32) b += n * sizeof(float4);
     b += (size_t)pl->bn() * pl->n_states * 12;
     for (const Buf* q : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef})
+                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef, &pl->subbest})
         b += q->cap;
     return (long)b;
 }

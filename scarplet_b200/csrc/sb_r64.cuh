@@ -260,7 +260,7 @@ SB_DEVICE void store_half(const float2 (&x)[R], int t, const float2* xch_partner
         const int m = t + R * uu;
         const int io = (m + dly) & (N - 1);
         const float2 a = FIELD == 0 ? mine : other, b = FIELD == 0 ? other : mine;
-        if (io < out_ny) sb_st_stream(dst + sb::gbuf_index(m, kx, kpitch), make_float4(a.y, a.x, b.y, b.x));
+        if (io < out_ny) sb_st_stream(dst + sb::gbuf_index(m, kx, kpitch), sb::gbuf_pack<float2, float4>(a, b));
     }
 }
 

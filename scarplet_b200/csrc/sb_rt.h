@@ -30,6 +30,7 @@ SB_DEVICE int sb_bx() { return blockIdx.x; }
 SB_DEVICE int sb_by() { return blockIdx.y; }
 SB_DEVICE int sb_bz() { return blockIdx.z; }
 SB_DEVICE int sb_nbx() { return gridDim.x; }
+SB_DEVICE int sb_nby() { return gridDim.y; }
 SB_DEVICE void sb_sync() { __syncthreads(); }
 // named barrier: `count` threads (a multiple of 32) of the block meet at barrier `id` (1..15)
 SB_DEVICE void sb_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -94,28 +95,6 @@ SB_DEVICE double sb_add(double a, double b) { return __dadd_rn(a, b); }
 SB_DEVICE double sb_sub(double a, double b) { return __dsub_rn(a, b); }
 SB_DEVICE double sb_div(double a, double b) { return __ddiv_rn(a, b); }
 
-// ---- TMA (bulk tensor copy engine): strided tiles between shared and global memory without
-// LSU instructions.  The descriptor is a CUtensorMap passed to the kernel by value
-// (__grid_constant__); one elected thread issues the copies.
-struct alignas(64) sb_tma_desc { unsigned char bytes[128]; };
-#define SB_GRID_CONSTANT __grid_constant__
-
-SB_DEVICE unsigned sb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-// make this thread's shared-memory writes visible to the copy engine (call before the barrier
-// that precedes the copy)
-SB_DEVICE void sb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// shared -> global, 3-D tile at coordinates (c0, c1, c2) (c0 fastest); bulk-group completion
-SB_DEVICE void sb_tma_store_3d(const sb_tma_desc* d, const void* smem_src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                 ::"l"(d), "r"(c0), "r"(c1), "r"(c2), "r"(sb_smem_addr(smem_src)) : "memory");
-}
-// close the group of copies issued so far and wait until they have READ their shared-memory
-// source (the CTA may then exit or reuse the buffer; global visibility follows at kernel end)
-SB_DEVICE void sb_tma_store_commit_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 typedef cudaStream_t sb_stream_t;
 
 #define SB_LAUNCH(kern, grid, block, smem, stream, ...) \
@@ -138,25 +117,6 @@ inline int sb_rt_memset(void* d, int v, size_t n, sb_stream_t s) {
 inline int sb_rt_sync(sb_stream_t s) { return (int)cudaStreamSynchronize(s); }
 inline int sb_rt_mem_info(size_t* free_b, size_t* total_b) { return (int)cudaMemGetInfo(free_b, total_b); }
 inline int sb_rt_last_error() { return (int)cudaGetLastError(); }
-// 3-D float32 tensor map: dims (elements, fastest first), strides in bytes of dims 1 and 2,
-// box (elements).  cuTensorMapEncodeTiled is fetched through the runtime, no -lcuda needed.
-inline int sb_rt_tma_encode_3d(sb_tma_desc* d, void* base, const unsigned long long dims[3],
-                               const unsigned long long strides_bytes[2], const unsigned box[3]) {
-    typedef int (*EncodeFn)(void*, int, unsigned, void*, const unsigned long long*, const unsigned long long*,
-                            const unsigned*, const unsigned*, int, int, int, int);
-    static EncodeFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
-            return (int)cudaErrorNotSupported;
-        fn = (EncodeFn)p;
-    }
-    const unsigned estr[3] = {1, 1, 1};
-    // CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7; interleave none, swizzle none, L2 promotion none, no OOB fill
-    const int r = fn(d, 7, 3, base, dims, strides_bytes, box, estr, 0, 0, 0, 0);
-    return r == 0 ? 0 : (int)cudaErrorInvalidValue;
-}
 typedef cudaEvent_t sb_event_t;
 inline int sb_rt_event_create(sb_event_t* e) { return (int)cudaEventCreate(e); }
 inline int sb_rt_event_destroy(sb_event_t e) { return (int)cudaEventDestroy(e); }

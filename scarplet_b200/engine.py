@@ -232,14 +232,18 @@ class Plan(object):
         return amp, snr
 
     # -- sweeps ------------------------------------------------------------------
-    def build_sweep(self, spec, scale, ages, angles, order="age_major", angle_slice=None):
+    def build_sweep(self, spec, scale, ages, angles, order="age_major", angle_slice=None, template_share=None):
         """Records for the fan-out over ``angles`` x ``ages``.
 
         ``order`` fixes the flat result index (the tie priority of ``compare``):
         ``"age_major"`` = ``match``'s hierarchical reduce (core.py:285-292),
         ``"angle_major"`` = ``calculate_best_fit_parameters_serial`` (core.py:116-134).
         ``angle_slice`` restricts the records to a contiguous shard of the angle list
-        (multi-GPU) without changing any index.
+        (multi-GPU) without changing any index.  ``template_share=(rank, world)`` cuts finer:
+        the orientation-major list of (orientation, scale, age) templates is split into
+        ``world`` contiguous shares that differ by at most one template (181 orientations
+        over 8 ranks are 23 / 22 whole orientations, 4 % apart; 5430 templates are 679 / 678),
+        an orientation at a cut being shared by two ranks.
         ``scale`` may be a sequence: one best state per scale (``Plan(states=len(scale))``),
         all scales of an orientation in the same sweep so that they share its curvature
         spectra; every state uses the same flat index space.
@@ -250,6 +254,16 @@ class Plan(object):
         scales = [scale] if np.ndim(scale) == 0 else list(scale)
         A, G = len(angles), len(ages)
         lo, hi = (0, A) if angle_slice is None else angle_slice
+        t_lo = t_hi = None
+        if template_share is not None:
+            rank, world = template_share
+            per_angle = G * len(scales)
+            base, extra = divmod(A * per_angle, world)
+            t_lo = rank * base + min(rank, extra)
+            t_hi = t_lo + base + (1 if rank < extra else 0)
+            lo, hi = t_lo // per_angle, -(-t_hi // per_angle)
+            if t_hi == t_lo:
+                lo = hi = 0
         ai, gi = np.meshgrid(np.arange(A), np.arange(G), indexing="ij")
         idx = gi * A + ai if order == "age_major" else ai * G + gi          # [A, G]
         age_of = np.empty(A * G, dtype=np.float64)
@@ -262,9 +276,11 @@ class Plan(object):
         recs = [P.template_records(spec, sc, ages, angles[lo:hi], self.nx, self.ny, self.dx,
                                    self.x, self.y, np.arange(hi - lo), idx[lo:hi], state=k)
                 for k, sc in enumerate(scales)]
-        arr_t = P.records_to_ctypes(np.stack(recs, axis=1))                 # [angle][scale][age]
-        n = (hi - lo) * G * len(scales)
-        return (arr_a, hi - lo), (arr_t, n), age_of, angle_of
+        recs = np.stack(recs, axis=1).reshape(-1) if hi > lo else np.zeros(0, dtype=P.TEMPLATE_DTYPE)   # [angle][scale][age]
+        if t_lo is not None:
+            recs = recs[t_lo - lo * G * len(scales): t_hi - lo * G * len(scales)]
+        arr_t = P.records_to_ctypes(recs)
+        return (arr_a, hi - lo), (arr_t, len(recs)), age_of, angle_of
 
     def reset(self):
         check(self.lib, self.lib.sb_best_reset(self._h))

@@ -180,6 +180,7 @@ SB_DEVICE int sb_bx() { return sbemu::current()->bx; }
 SB_DEVICE int sb_by() { return sbemu::current()->by; }
 SB_DEVICE int sb_bz() { return sbemu::current()->bz; }
 SB_DEVICE int sb_nbx() { return (int)sbemu::current()->grid.x; }
+SB_DEVICE int sb_nby() { return (int)sbemu::current()->grid.y; }
 // named barrier: `count` threads of the block meet at barrier `id` (1..15); id 0 with count 0
 // is the block-wide barrier over the threads that are still running
 SB_DEVICE void sb_bar(int id, int count) {
@@ -208,37 +209,6 @@ SB_DEVICE double sb_mul(double a, double b) { return a * b; }
 SB_DEVICE double sb_add(double a, double b) { return a + b; }
 SB_DEVICE double sb_sub(double a, double b) { return a - b; }
 SB_DEVICE double sb_div(double a, double b) { return a / b; }
-
-// TMA stand-in: the descriptor holds the tensor geometry, the copy is a loop run by the
-// issuing fiber
-struct alignas(64) sb_tma_desc { unsigned char bytes[128]; };
-struct sb_emu_tmap { float* base; unsigned long long dims[3]; unsigned long long strides[2]; unsigned box[3]; };
-static_assert(sizeof(sb_emu_tmap) <= sizeof(sb_tma_desc), "descriptor size");
-#define SB_GRID_CONSTANT
-SB_DEVICE void sb_fence_async_smem() {}
-SB_DEVICE void sb_tma_store_3d(const sb_tma_desc* d, const void* smem_src, int c0, int c1, int c2) {
-    sb_emu_tmap m;
-    std::memcpy(&m, d->bytes, sizeof(m));
-    const float* src = (const float*)smem_src;
-    for (unsigned k = 0; k < m.box[2]; ++k)
-        for (unsigned j = 0; j < m.box[1]; ++j)
-            for (unsigned i = 0; i < m.box[0]; ++i, ++src) {
-                const unsigned long long x = c0 + i, y = c1 + j, z = c2 + k;
-                if (x >= m.dims[0] || y >= m.dims[1] || z >= m.dims[2]) continue;    // out of bounds: not written
-                *(float*)((char*)m.base + x * 4 + y * m.strides[0] + z * m.strides[1]) = *src;
-            }
-}
-SB_DEVICE void sb_tma_store_commit_wait_read() {}
-inline int sb_rt_tma_encode_3d(sb_tma_desc* d, void* base, const unsigned long long dims[3],
-                               const unsigned long long strides_bytes[2], const unsigned box[3]) {
-    sb_emu_tmap m;
-    m.base = (float*)base;
-    for (int i = 0; i < 3; ++i) { m.dims[i] = dims[i]; m.box[i] = box[i]; }
-    m.strides[0] = strides_bytes[0]; m.strides[1] = strides_bytes[1];
-    std::memset(d->bytes, 0, sizeof(d->bytes));
-    std::memcpy(d->bytes, &m, sizeof(m));
-    return 0;
-}
 
 typedef void* sb_stream_t;
 

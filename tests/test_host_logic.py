@@ -181,3 +181,29 @@ def test_bulk_template_records_equal_single(ny, nx, de, cls, scale, ages):
             assert tuple(getattr(one, n) for n, _ in SbTemplate._fields_) == tuple(recs[a, g].tolist())
     arr = P.records_to_ctypes(recs)
     assert arr[G + 1].idx == idx[1, 1 % G] if G > 1 else arr[1].idx == idx[1, 0]
+
+
+def test_template_shares_partition_the_search():
+    """``build_sweep(template_share=(rank, world))``: the ranks' records are a partition of the
+    whole search (orientation-major), sizes differ by at most one template, indices unchanged."""
+    class FakePlan(object):
+        nx, ny, dx = 64, 64, 1.0
+        x, y = P.axis_vectors(64, 64, 1.0)
+    from scarplet_b200.engine import Plan
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)
+    ages = np.logspace(0, 3.5, 30)
+    _, (full, n_full), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major")
+    assert n_full == 181 * 30 * 2
+    for world in (1, 2, 8, 7):
+        seen, sizes = [], []
+        for rank in range(world):
+            (a, na), (t, nt), _, _ = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major",
+                                                      template_share=(rank, world))
+            sizes.append(nt)
+            for k in range(nt):
+                assert 0 <= t[k].angle_id < na
+                seen.append((t[k].idx, t[k].state, round(angle_of[t[k].idx], 12)))
+                # the angle record the template points at is its own orientation
+                assert np.isclose(a[t[k].angle_id].cos_a, np.cos(angle_of[t[k].idx]))
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n_full
+        assert seen == [(full[k].idx, full[k].state, round(angle_of[full[k].idx], 12)) for k in range(n_full)]
