@@ -567,12 +567,11 @@ template <int N>
 SB_GLOBAL SB_LAUNCH_BOUNDS((N / E > 256 ? N / E : 256), (N / E > 256 ? 1 : 2))
 k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RESTRICT fit,
              const float4* SB_RESTRICT gbuf, float* SB_RESTRICT best_snr, float* SB_RESTRICT best_amp, int* best_idx,
-             const float2* SB_RESTRICT tw, const int4* SB_RESTRICT cross, float* sub_snr, float* sub_amp, int* sub_idx,
-             long sub_stride) {
+             const float2* SB_RESTRICT tw, const int4* SB_RESTRICT cross, long sub_stride) {
     // grid.y > 1 (small rasters, whose row pairs alone do not fill the GPU): the templates of the
-    // launch are dealt round-robin to grid.y sub-streams; sub-stream 0 folds into the best state
-    // itself, sub-stream j > 0 into its own copy (sub_* + (j - 1) * sub_stride), and k_best_fold
-    // merges the copies after the sweep.
+    // launch are dealt round-robin to grid.y sub-streams; sub-stream j folds into copy j of the
+    // best state (best_* + j * sub_stride; copy 0 is the state itself) and k_best_fold merges the
+    // copies after the sweep.
     // `slots` (optional): the `count` batch slots this launch folds -- the templates of one best
     // state (template scale) inside a batch that mixes several; null: slots 0 .. count - 1.
     // best_*: the state's planes, offset so that raster row gi is at gi * nx (row slabs).
@@ -640,11 +639,9 @@ k_fit_rows_g(Geom g, int count, const int* SB_RESTRICT slots, const FitT* SB_RES
     c.nx = g.nx;
     c.s_fit = s_fit;
     c.dbg = g.dbg;
-    if (sb_by() > 0) {
-        best_snr = sub_snr + (sb_by() - 1) * sub_stride;
-        best_amp = sub_amp + (sb_by() - 1) * sub_stride;
-        best_idx = sub_idx + (sb_by() - 1) * sub_stride;
-    }
+    best_snr += sb_by() * sub_stride;
+    best_amp += sb_by() * sub_stride;
+    best_idx += sb_by() * sub_stride;
     c.best_amp = best_amp;
     c.best_idx = best_idx;
     c.cross = cross;

@@ -89,12 +89,13 @@ struct sb_plan {
     double* d_x = nullptr;
     double* d_y = nullptr;
     int n_states = 1;               // best states (one per template scale in a multi-scale search)
-    float* d_bsnr = nullptr;        // [n_states][slab rows][nx]
+    int best_copies = 1;            // copies of the best state (sub-streams of the fit kernel on small rasters)
+    float* d_bsnr = nullptr;        // [best_copies][n_states][slab rows][nx]; copy 0 is the state
     float* d_bamp = nullptr;
     int* d_bidx = nullptr;
     std::map<long, void*> tw;      // twiddle tables keyed by 2 * n + (float64 ? 1 : 0)
     int precision = 32;            // 32: complex64 pipeline, 64: complex128 pipeline
-    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux, spec9, coef, subbest;
+    Buf cr, fct, trt, part, gbuf, sums, fit, tmpls, angles, tables, raw, tbox, slots, cross, casa, aux, spec9, coef;
     int fit_substreams = 0;        // 0: automatic (small rasters), else the number of sub-streams of the fit kernel
     int fast = 1;                  // 1: pipelined complex64 kernels (sb_fast.cuh), 0: simple kernels
     // persistent column kernel: 1 always, 0 never, -1 (default) when a search angle carries at least
@@ -304,6 +305,7 @@ int alloc_best(sb_plan* pl) {
     for (void* p : {(void*)pl->d_bsnr, (void*)pl->d_bamp, (void*)pl->d_bidx})
         if (p) sb_rt_free(p);
     pl->d_bsnr = nullptr; pl->d_bamp = nullptr; pl->d_bidx = nullptr;
+    pl->best_copies = 1;
     const size_t n = (size_t)pl->bn() * pl->n_states;
     int e = 0;
     e |= sb_rt_malloc((void**)&pl->d_bsnr, n * sizeof(float));
@@ -352,12 +354,14 @@ int ensure_diffs64(sb_plan* pl) {
     return 0;
 }
 
-// relative cost per point of the per-template kernels at FFT length P, measured (bench.py, one
-// B200): 4096 has the radix-64 column kernel; 8192 needs a fourth exchange stage and has no
-// persistent column kernel (C4 at 8192 periodic: 1.9 x the time per pixel of C3 at 4096)
+// relative cost per point and AXIS of the per-template kernels at FFT length P (the cost of a tile
+// is the product over its two axes), measured (bench.py, one B200): 4096 has the radix-64 column
+// kernel; 8192 needs a fourth exchange stage and has no persistent column kernel -- C4 on its
+// periodic 8192^2 domain takes 1.36 x the time per pixel of C3 on 4096^2 (1.17 per axis), and
+// 9 % less than on 3 x 3 padded tiles of 4096 / 2048
 double length_weight(int P) {
     switch (P) {
-        case 8192: return 1.9;
+        case 8192: return 1.2;
         case 4096: return 1.0;
         case 2048: return 1.1;
         case 1024: return 1.15;
@@ -680,10 +684,24 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
     }
     const long sub_stride = bn_all(pl);
     if (nsub > 1) {
-        const size_t cnt_x = (size_t)(nsub - 1) * sub_stride;
-        SB_OK(ensure(pl->subbest, cnt_x * 12));
-        SB_LAUNCH(sb::k_best_init, dim3(div_up((long)cnt_x, 256)), dim3(256), 0, pl->stream, (long)cnt_x, (float*)pl->subbest.p,
-                  (float*)pl->subbest.p + cnt_x, (int*)((float*)pl->subbest.p + 2 * cnt_x));
+        if (nsub > pl->best_copies) {
+            // grow the best-state arrays to nsub copies, keeping copy 0 (the accumulated state)
+            float *s2 = nullptr, *a2 = nullptr;
+            int* i2 = nullptr;
+            const size_t n1 = (size_t)sub_stride, nn = n1 * nsub;
+            if (sb_rt_malloc((void**)&s2, nn * 4) || sb_rt_malloc((void**)&a2, nn * 4) || sb_rt_malloc((void**)&i2, nn * 4))
+                return fail("out of device memory (best-state copies)");
+            SB_TRY(sb_rt_d2d(s2, pl->d_bsnr, n1 * 4, pl->stream));
+            SB_TRY(sb_rt_d2d(a2, pl->d_bamp, n1 * 4, pl->stream));
+            SB_TRY(sb_rt_d2d(i2, pl->d_bidx, n1 * 4, pl->stream));
+            SB_TRY(sb_rt_sync(pl->stream));
+            sb_rt_free(pl->d_bsnr); sb_rt_free(pl->d_bamp); sb_rt_free(pl->d_bidx);
+            pl->d_bsnr = s2; pl->d_bamp = a2; pl->d_bidx = i2;
+            pl->best_copies = nsub;
+        }
+        const long cnt_x = (long)(nsub - 1) * sub_stride;
+        SB_LAUNCH(sb::k_best_init, dim3(div_up(cnt_x, 256)), dim3(256), 0, pl->stream, cnt_x, pl->d_bsnr + sub_stride,
+                  pl->d_bamp + sub_stride, pl->d_bidx + sub_stride);
         SB_OK(check_launch(pl, "k_best_init"));
     }
 
@@ -911,16 +929,13 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
                                     constexpr int N = decltype(nn)::value;
                                     using S = Shape<N, float>;
                                     ProfScope prof(pl, K_FIT_ROWS);
+                                    // (a variant without the get_err_mask members spills MORE: 564 bytes against 312)
                                     auto kern = sb::k_fit_rows_g<N>;
                                     SB_ALLOW_SMEM(kern, S::smem_fit_f);
-                                    const size_t cnt_x = (size_t)(nsub - 1) * sub_stride;
-                                    float* xs = nsub > 1 ? (float*)pl->subbest.p + (long)gp.state * bn - boff : nullptr;
                                     SB_LAUNCH(kern, dim3(div_up(Py / 2, S::GP), nsub), dim3(S::threads), S::smem_fit_f,
                                               pl->stream, g, gp.count, d_slots, (const sb::FitT*)pl->fit.p,
                                               (const float4*)pl->gbuf.p, bsnr, bamp, bidx, (const float2*)twx,
-                                              gp.err ? (const int4*)pl->cross.p : (const int4*)nullptr, xs,
-                                              nsub > 1 ? xs + cnt_x : nullptr, nsub > 1 ? (int*)(xs + 2 * cnt_x) : nullptr,
-                                              sub_stride);
+                                              gp.err ? (const int4*)pl->cross.p : (const int4*)nullptr, sub_stride);
                                     return check_launch(pl, "k_fit_rows_g");
                                 }));
                                 if (g.poison) {
@@ -950,10 +965,9 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
             }
         }
     if (nsub > 1) {
-        const size_t cnt_x = (size_t)(nsub - 1) * sub_stride;
-        const float* xs = (const float*)pl->subbest.p;
         SB_LAUNCH(sb::k_best_fold, dim3(div_up(sub_stride, 256)), dim3(256), 0, pl->stream, sub_stride, nsub - 1, sub_stride,
-                  xs, xs + cnt_x, (const int*)(xs + 2 * cnt_x), pl->d_bsnr, pl->d_bamp, pl->d_bidx);
+                  (const float*)pl->d_bsnr + sub_stride, (const float*)pl->d_bamp + sub_stride,
+                  (const int*)pl->d_bidx + sub_stride, pl->d_bsnr, pl->d_bamp, pl->d_bidx);
         SB_OK(check_launch(pl, "k_best_fold"));
     }
     drain_profile(pl);
@@ -1046,7 +1060,7 @@ int sb_plan_destroy(sb_plan* pl) {
     for (auto& kv : pl->tw) sb_rt_free(kv.second);
     for (auto e : pl->ev_pool) sb_rt_event_destroy(e);
     for (Buf* b : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef, &pl->subbest})
+                   &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef})
         release(*b);
 #ifndef SB_EMU
     if (pl->own_stream) cudaStreamDestroy(pl->stream);
@@ -1135,9 +1149,9 @@ long sb_plan_device_bytes(const sb_plan* pl) {
     if (pl->d_dem && pl->own_dem) b += n * sizeof(double);
     if (pl->d_diffs) b += n * 3 * sizeof(double);
     if (pl->d_diffs32) b += n * sizeof(float4);
-    b += (size_t)pl->bn() * pl->n_states * 12;
+    b += (size_t)pl->bn() * pl->n_states * pl->best_copies * 12;
     for (const Buf* q : {&pl->cr, &pl->fct, &pl->trt, &pl->part, &pl->gbuf, &pl->sums, &pl->fit, &pl->tmpls, &pl->angles,
-                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef, &pl->subbest})
+                         &pl->tables, &pl->raw, &pl->tbox, &pl->slots, &pl->cross, &pl->casa, &pl->aux, &pl->spec9, &pl->coef})
         b += q->cap;
     return (long)b;
 }
