@@ -145,6 +145,13 @@ int sb_best_reset(sb_plan* plan);
 int sb_sweep(sb_plan* plan, const sb_angle* angles, int n_angles,
              const sb_template* tmpls, int n_tmpls);
 
+/* The same for a SHARE of a larger search (one rank's orientations): whole_search5 =
+ * {sy_lo, sy_hi, sx_lo, sx_hi of the union of all support boxes, templates per orientation} of
+ * the undivided search.  FFT domains, tiles and kernel variants are then chosen exactly as the
+ * undivided search chooses them, which makes the shares' results bit-identical to its. */
+int sb_sweep_ex(sb_plan* plan, const sb_angle* angles, int n_angles, const sb_template* tmpls, int n_tmpls,
+                const int32_t* whole_search5);
+
 /* Decode the best state to the reference's stack order [amp, age, angle, snr]
  * (core.py:190-193): out4 is float64[4*ny*nx]; age_of/angle_of are host float64
  * tables indexed by sb_template.idx (n_idx entries). */

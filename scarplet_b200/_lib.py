@@ -76,6 +76,8 @@ def _declare(lib):
                                       c_void_p, c_int]
     lib.sb_best_reset.argtypes = [P]
     lib.sb_sweep.argtypes = [P, POINTER(SbAngle), c_int, POINTER(SbTemplate), c_int]
+    lib.sb_sweep_ex.argtypes = [P, POINTER(SbAngle), c_int, POINTER(SbTemplate), c_int, POINTER(c_int32)]
+    lib.sb_sweep_ex.restype = c_int
     lib.sb_finalize.argtypes = [P, c_void_p, c_void_p, c_int, c_void_p, c_int]
     lib.sb_best_state.argtypes = [P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.sb_best_pack.argtypes = [P, c_void_p]
@@ -110,7 +112,7 @@ EXPORTED = ("sb_last_error", "sb_build_info", "sb_plan_create", "sb_plan_destroy
             "sb_debug_fft", "sb_sync", "sb_plan_set_slab", "sb_plan_dem_rows", "sb_plan_curv_stats",
             "sb_plan_set_curv_stats", "sb_plan_stream", "sb_plan_device_bytes", "sb_plan_last_fft_area",
             "sb_finalize_ex", "sb_best_state_ex", "sb_best_merge", "sb_curvature_noise_moments",
-            "sb_fill_nodata", "sb_debug_fft_bench")
+            "sb_fill_nodata", "sb_debug_fft_bench", "sb_sweep_ex")
 
 
 def library_path():

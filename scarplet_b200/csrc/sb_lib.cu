@@ -493,7 +493,7 @@ struct AngleBatch {
 
 template <typename R>
 int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in, int n_tmpls,
-                SweepOut so) {
+                SweepOut so, const int32_t* hint) {
     typedef typename Vec<R>::v2 C2;
     typedef typename Vec<R>::v4 C4;
     if (!pl->d_dem) return fail("no DEM set (sb_set_dem_host / sb_set_dem_dev)");
@@ -528,6 +528,13 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
         syp = std::max(syp, t.sy_hi - t.sy_lo + 1);
         any_err |= t.errmode != 0;
         multi_state |= t.state != tm[0].state;
+    }
+    if (hint) {
+        // the extents of the WHOLE search this sweep is a share of: FFT domains, tiles and kernel
+        // variants are then chosen exactly as the undivided search chooses them
+        lo_y = std::min(lo_y, hint[0]); hi_y = std::max(hi_y, hint[1]);
+        lo_x = std::min(lo_x, hint[2]); hi_x = std::max(hi_x, hint[3]);
+        syp = std::max(syp, hint[1] - hint[0] + 1);
     }
     syp += syp & 1;      // the row kernels store row pairs
     AxisPlan ay, ax;
@@ -572,6 +579,7 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
         max_per_angle = std::max(max_per_angle, first[a + 1]);
         first[a + 1] += first[a];
     }
+    if (hint) max_per_angle = std::max(max_per_angle, hint[4]);
     int Bt = (int)std::max<size_t>(1, std::min<size_t>(64, (budget * 6 / 10) / per_tmpl));
     int Ba = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_angles, (budget * 4 / 10) / per_angle));
     Ba = std::min(Ba, 64);
@@ -975,9 +983,9 @@ int run_sweep_t(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_temp
 }
 
 int run_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls_in, int n_tmpls,
-              SweepOut so) {
-    if (pl->precision == 64) return run_sweep_t<double>(pl, angles, n_angles, tmpls_in, n_tmpls, so);
-    return run_sweep_t<float>(pl, angles, n_angles, tmpls_in, n_tmpls, so);
+              SweepOut so, const int32_t* hint = nullptr) {
+    if (pl->precision == 64) return run_sweep_t<double>(pl, angles, n_angles, tmpls_in, n_tmpls, so, hint);
+    return run_sweep_t<float>(pl, angles, n_angles, tmpls_in, n_tmpls, so, hint);
 }
 
 int copy_out(sb_plan* pl, double* dst, const double* src_dev, size_t count, int out_is_device) {
@@ -1300,6 +1308,12 @@ int sb_best_reset(sb_plan* pl) {
 int sb_sweep(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls, int n_tmpls) {
     if (!pl || !angles || !tmpls) return fail("sb_sweep: null");
     return run_sweep(pl, angles, n_angles, tmpls, n_tmpls, SweepOut());
+}
+
+int sb_sweep_ex(sb_plan* pl, const sb_angle* angles, int n_angles, const sb_template* tmpls, int n_tmpls,
+                const int32_t* whole_search5) {
+    if (!pl || !angles || !tmpls) return fail("sb_sweep_ex: null");
+    return run_sweep(pl, angles, n_angles, tmpls, n_tmpls, SweepOut(), whole_search5);
 }
 
 int sb_finalize_ex(sb_plan* pl, int state, int row_lo, int row_hi, const double* age_of_host,

@@ -280,17 +280,25 @@ class Plan(object):
         if t_lo is not None:
             recs = recs[t_lo - lo * G * len(scales): t_hi - lo * G * len(scales)]
         arr_t = P.records_to_ctypes(recs)
-        return (arr_a, hi - lo), (arr_t, len(recs)), age_of, angle_of
+        whole = None
+        if (lo, hi) != (0, A) or t_lo is not None:
+            # a share of a larger search: the extents of the whole one, so that FFT domains, tiles and
+            # kernel variants are chosen as the undivided search chooses them (sb_sweep_ex)
+            ext = [P.support_extents(spec, sc, ages, angles, self.nx, self.ny, self.dx) for sc in scales]
+            whole = (c_int * 5)(min(e[0] for e in ext), max(e[1] for e in ext), min(e[2] for e in ext),
+                                max(e[3] for e in ext), G * len(scales))
+        return (arr_a, hi - lo), (arr_t, len(recs), whole), age_of, angle_of
 
     def reset(self):
         check(self.lib, self.lib.sb_best_reset(self._h))
 
     def sweep(self, angle_records, template_records):
         arr_a, na = angle_records
-        arr_t, nt = template_records
+        arr_t, nt = template_records[0], template_records[1]
+        whole = template_records[2] if len(template_records) > 2 else None
         if nt == 0:
             return
-        check(self.lib, self.lib.sb_sweep(self._h, arr_a, na, arr_t, nt))
+        check(self.lib, self.lib.sb_sweep_ex(self._h, arr_a, na, arr_t, nt, whole))
 
     # -- results -----------------------------------------------------------------
     def _result_array(self, rows):

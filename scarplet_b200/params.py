@@ -209,6 +209,26 @@ def template_records(spec, scale, ages, angles, nx, ny, de, x, y, angle_ids, idx
     return out
 
 
+def support_extents(spec, scale, ages, angles, nx, ny, de):
+    """(sy_lo, sy_hi, sx_lo, sx_hi): union of the support boxes of ``template_records`` over
+    ``angles`` x ``ages`` (the same arithmetic, without building the records)."""
+    ages = np.atleast_1d(np.asarray(ages, dtype=np.float64))
+    angles = np.asarray(angles, dtype=np.float64)
+    alpha = [-float(a) for a in angles]
+    ca = np.array([float(np.cos(a)) for a in alpha])[:, None]
+    sa = np.array([float(np.sin(a)) for a in alpha])[:, None]
+    c_eff = np.array([_age_scalars(spec, float(age), nx, de)[3] for age in ages], dtype=np.float64)[None, :]
+    d = float(scale)
+    step = abs(float(de))
+    ex = (c_eff * np.abs(ca) + d * np.abs(sa)) / step
+    ey = (c_eff * np.abs(sa) + d * np.abs(ca)) / step
+    a0, b0 = ny // 2, nx // 2
+    rx = np.minimum(ex, 4.0 * nx).astype(np.int64) + 2
+    ry = np.minimum(ey, 4.0 * ny).astype(np.int64) + 2
+    return (int(np.maximum(-ry, -a0).min()), int(np.minimum(ry, ny - 1 - a0).max()),
+            int(np.maximum(-rx, -b0).min()), int(np.minimum(rx, nx - 1 - b0).max()))
+
+
 def records_to_ctypes(records):
     """Flat ctypes ``SbTemplate`` array (what ``sb_sweep`` takes) from a structured array."""
     flat = np.ascontiguousarray(records).reshape(-1)

@@ -278,3 +278,32 @@ def test_noise_level_and_nodata_fill(cuda_lib):
     grid._fill_nodata()
     assert not np.isnan(grid._griddata).any()
     assert np.allclose(grid._griddata, O.fill_nodata(holes), rtol=1e-12, atol=0)
+
+
+def test_template_shares_accumulate_to_the_single_search(cuda_lib):
+    """What the ranks of an orientation-sharded search compute, one share after the other on one
+    device into the same best state: bit-identical to the single sweep.  An orientation's
+    curvature spectra, a template's correlation and fit must not depend on where in a batch they
+    are computed (the merged multi-GPU result is then bit-identical too: scratch/mgpu_check.py)."""
+    from scarplet_b200 import params as P
+    from scarplet_b200.engine import Plan
+    from scarplet_b200.synth import synthetic_dem
+    from scarplet_b200.templates import Channel, Scarp
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)
+    for spec, n, nx, scale, ages in ((Scarp._sb_spec, 1024, 1024, 50, [3.0, 30.0, 300.0]),
+                                     (Channel._sb_spec, 701, 701, 10, [0.1]),
+                                     (Scarp._sb_spec, 4096, 384, 60, [2.0, 9.0, 40.0, 180.0, 800.0])):
+        z = synthetic_dem(n, seed=11, nx=nx)
+        with Plan(n, nx, 1.0, 1.0) as plan:
+            plan.set_dem(z)
+            a, t, age_of, angle_of = plan.build_sweep(spec, scale, ages, angles)
+            plan.reset()
+            plan.sweep(a, t)
+            single = plan.finalize(age_of, angle_of)
+            for world in (8, 3):
+                plan.reset()
+                for rank in range(world):
+                    a, t, _, _ = plan.build_sweep(spec, scale, ages, angles, template_share=(rank, world))
+                    plan.sweep(a, t)
+                shares = plan.finalize(age_of, angle_of)
+                assert np.array_equal(shares, single), (n, nx, world)

@@ -99,12 +99,12 @@ def test_sweep_index_orders():
     from scarplet_b200.engine import Plan
     angles = P.search_angles(-0.05, 0.05)
     ages = [1.0, 10.0, 100.0]
-    (a, na), (t, nt), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, 8, ages, angles, "age_major")
+    (a, na), (t, nt, _w), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, 8, ages, angles, "age_major")
     assert na == len(angles) and nt == len(angles) * 3
     for k in range(nt):
         assert age_of[t[k].idx] == ages[k % 3] and angle_of[t[k].idx] == angles[t[k].angle_id]
         assert t[k].idx == (k % 3) * len(angles) + t[k].angle_id
-    (a, na), (t, nt), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, 8, ages, angles, "angle_major",
+    (a, na), (t, nt, _w), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, 8, ages, angles, "angle_major",
                                                           angle_slice=(2, 5))
     assert na == 3 and nt == 9 and [t[k].idx for k in range(nt)] == list(range(6, 15))
 
@@ -192,12 +192,12 @@ def test_template_shares_partition_the_search():
     from scarplet_b200.engine import Plan
     angles = P.search_angles(-np.pi / 2, np.pi / 2)
     ages = np.logspace(0, 3.5, 30)
-    _, (full, n_full), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major")
+    _, (full, n_full, _w), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major")
     assert n_full == 181 * 30 * 2
     for world in (1, 2, 8, 7):
         seen, sizes = [], []
         for rank in range(world):
-            (a, na), (t, nt), _, _ = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major",
+            (a, na), (t, nt, _w), _, _ = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major",
                                                       template_share=(rank, world))
             sizes.append(nt)
             for k in range(nt):
