@@ -64,7 +64,7 @@ typedef struct sb_template {
 #define SB_PLAN_DEFAULT 0u
 
 const char* sb_last_error(void);
-/* library / build information: "cuda sm_100a" for the product build */
+/* library / build information: "cuda sm_100a <hash of the sources it was compiled from>" for the product build */
 const char* sb_build_info(void);
 
 /* Plan = raster geometry + device workspace.  dx2/dy2 are `dx ** 2`, `dy ** 2` as the

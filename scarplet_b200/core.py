@@ -71,15 +71,22 @@ def _plan_for(data, states=1):
             if k == key:
                 plan = _cache.pop(i)[1]
                 break
-    if plan is None:
-        plan = Plan(ny, nx, dx, dy)
-    try:
-        if plan.states != states:
-            plan.set_states(states)
-        plan.set_dem(z)
-    except Exception:
-        plan.close()
-        raise
+    for attempt in (0, 1):
+        try:
+            if plan is None:
+                plan = Plan(ny, nx, dx, dy)
+            if plan.states != states:
+                plan.set_states(states)
+            plan.set_dem(z)
+            break
+        except engine.SbError:
+            # most likely device memory held by cached plans of other shapes: drop them, try once more
+            if plan is not None:
+                plan.close()
+                plan = None
+            if attempt == 1:
+                raise
+            release()
     return _Lease(key, plan)
 
 

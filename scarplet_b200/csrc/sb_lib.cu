@@ -1003,11 +1003,15 @@ extern "C" {
 
 const char* sb_last_error(void) { return g_err.c_str(); }
 
+#ifndef SB_SOURCE_HASH
+#define SB_SOURCE_HASH "unhashed"
+#endif
+
 const char* sb_build_info(void) {
 #ifdef SB_EMU
     return "cpu-emulator (test infrastructure)";
 #else
-    return "cuda sm_100a";
+    return "cuda sm_100a " SB_SOURCE_HASH;
 #endif
 }
 

@@ -10,7 +10,7 @@ from ctypes import byref, c_double, c_int, c_long, c_void_p
 import numpy as np
 
 from . import _lib
-from ._lib import SbAngle, SbTemplate, check
+from ._lib import SbAngle, SbError, SbTemplate, check  # noqa: F401
 from . import params as P
 
 

@@ -25,7 +25,8 @@ def _templates():
 
 
 def test_library_is_cuda(cuda_lib):
-    assert cuda_lib.sb_build_info() == b"cuda sm_100a"
+    import __graft_entry__
+    assert cuda_lib.sb_build_info() == ("cuda sm_100a " + __graft_entry__.source_hash()).encode()
 
 
 @pytest.mark.parametrize("n", [128, 256, 512, 1024, 2048, 4096, 8192])
