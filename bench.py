@@ -271,19 +271,23 @@ def device_dem_rows(n, seed, row0, nrows, device, relief=30.0, tile=4096):
 # ---------------------------------------------------------------------------
 # roofline bookkeeping
 # ---------------------------------------------------------------------------
-def algorithmic_bytes(kernel, tpa, batch):
+def algorithmic_bytes(kernel, tpa, batch, n_angles=181, angle_batch=64):
     """HBM bytes one template-pixel evaluation needs from each kernel of the complex64 schedule
     (``tpa`` = templates per orientation, ``batch`` = templates per fold
     launch).  Half spectra: a plane of Py x (Px/2+1) complex values is 4 B per pixel and field."""
     if kernel == "k_curv_rows":
-        return (16.0 + 8.0) / tpa        # read dxx,dxy,dyy float4 (16), write both row spectra (8); once per angle
+        # once per FFT tile: five packed plane pairs through a row pass (read 16, write 8) and a
+        # column pass (read 8, write 8) -- k_diff_rows_f + k_curv_cols
+        return 5 * (16.0 + 8.0 + 8.0 + 8.0) / (tpa * n_angles)
     if kernel == "k_curv_cols":
-        return (8.0 + 8.0) / tpa         # read row spectra (8), write F[curv], F[curv^2] (8); once per angle
+        # k_combine_spectra: nine planes read once per batch of orientations (36 B/px), both spectra
+        # of every orientation written (8 B/px)
+        return (36.0 / max(angle_batch, 1) + 8.0) / tpa
     if kernel == "k_tmpl_rows":
         return 0.6                       # the template's row spectra on its support rows only
     if kernel == "k_conv_cols":
         # write both inverse-column planes (8); the curvature-spectrum columns are staged in shared
-        # memory once per run of same-angle templates by the persistent kernel (8 / tpa), else per template
+        # memory once per run of same-angle templates by the persistent kernels (8 / tpa), else per template
         return 8.0 + (8.0 / tpa if tpa >= 4 else 8.0) + 0.6
     if kernel == "k_fit_rows":
         return 8.0 + 12.0 / max(batch, 1)    # read both planes (8) + best-state read-modify-write per launch
@@ -514,10 +518,11 @@ def run_ours(args):
     for k, (ms, cnt) in prof.items():
         if cnt == 0:
             continue
-        b = algorithmic_bytes(k, tpa, batch) * my_evals
+        ab_k = algorithmic_bytes(k, tpa, batch, len(angles), geo["angle_batch"])
+        b = ab_k * my_evals
         total_bytes += b
         entry = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
-                 "algorithmic_bytes_per_px_eval": algorithmic_bytes(k, tpa, batch),
+                 "algorithmic_bytes_per_px_eval": ab_k,
                  "algorithmic_GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None,
                  "algorithmic_frac": b / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
                  "share_of_step": ms / total_ms if total_ms else None}

@@ -147,20 +147,27 @@ struct ConvCtx {
 #endif
         if constexpr (P == K - 1 && F == 1) {
             if (dst) {
+                // row m = t + q T lies at gbuf_index(t, kx) + q * T * kpitch (T is even): one pointer,
+                // one add per store
+                static_assert(kGbufRows == 2 && T % 2 == 0, "row-pair interleave");
+                const long step = (long)T * kpitch;
+                float4* p = dst + gbuf_index(t, kx, kpitch);
+                const int io0 = t + dly;
 #pragma unroll
                 for (int q = 0; q < E; ++q) {
-                    const int io = (t + q * T + dly) & (N - 1);
 #ifdef SB_CONV_KEEP_A
                     const float2 a = va_fin[q];      // field a's result, still in the caller's registers
 #else
                     const float2 a = smA[t + q * T];
 #endif
                     if (SB_DBG_ON(dbg, 1) && v[q].x != 1.2345e-30f) continue;
+                    const float4 out = gbuf_pack<float2, float4>(a, v[q]);
                     if (SB_DBG_ON(dbg, 128)) {      // timing only: same bytes, fully coalesced
-                        sb_st_stream(dst + ((long)kx * N + t + q * T), gbuf_pack<float2, float4>(a, v[q]));
+                        sb_st_stream(dst + ((long)kx * N + t + q * T), out);
                         continue;
                     }
-                    if (io < out_ny) sb_st_stream(dst + gbuf_index(t + q * T, kx, kpitch), gbuf_pack<float2, float4>(a, v[q]));
+                    if (((io0 + q * T) & (N - 1)) < out_ny) sb_st_stream(p, out);
+                    p += step;
                 }
             }
         }

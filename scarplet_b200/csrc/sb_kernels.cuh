@@ -128,6 +128,16 @@ SB_DEVICE C4 gbuf_pack(const C2 a, const C2 b) {
     return r;
 }
 
+#ifdef SB_F32X2
+// the same in two packed adds: (a.x, a.y) + (b.y, -b.x) and (b.y, b.x) + (-a.x, a.y)
+template <>
+SB_DEVICE float4 gbuf_pack<float2, float4>(const float2 a, const float2 b) {
+    const float2 d = sbfft::unpk(sbfft::add2(sbfft::pk(a), sbfft::pk(b.y, -b.x)));
+    const float2 m = sbfft::unpk(sbfft::add2(sbfft::pk(b.y, b.x), sbfft::pk(-a.x, a.y)));
+    return make_float4(d.x, d.y, m.x, m.y);
+}
+#endif
+
 SB_DEVICE long gbuf_index(int m, int kx, int kpitch) {
     return ((long)(m / kGbufRows) * kpitch + kx) * kGbufRows + (m % kGbufRows);
 }

@@ -248,19 +248,34 @@ SB_DEVICE void park_half(const float2 (&x)[R], int t, float2* xch) {
     for (int u = 0; u < R / 2; ++u) xch[(u + HALF * (R / 2)) * R + t] = x[slot(u + HALF * (R / 2))];
 }
 // store rows u = 32 HALF .. of both fields: mine from registers, the partner's from its buffer.
-// FIELD: which of the two fields is mine.  Swapped back (inverse via forward) on the way out.
+// FIELD: which of the two fields is mine.  Row m = t + 64 u lies at gbuf_index(t, kx) + u * 64 * kpitch
+// (m / 2 = t / 2 + 32 u): one pointer, one add per store; in a periodic domain every row is stored.
 template <int HALF, int FIELD>
 SB_DEVICE void store_half(const float2 (&x)[R], int t, const float2* xch_partner, float4* dst, int kx, int kpitch,
                           int dly, int out_ny) {
+    static_assert(sb::kGbufRows == 2, "store_half: row-pair interleave");
+    const long step = (long)R * kpitch;
+    float4* p = dst + sb::gbuf_index(t, kx, kpitch) + (long)(HALF * (R / 2)) * step;
+    if (out_ny >= N) {
 #pragma unroll
-    for (int u = 0; u < R / 2; ++u) {
-        const int uu = u + HALF * (R / 2);
-        const float2 mine = x[slot(uu)];
-        const float2 other = xch_partner[uu * R + t];
-        const int m = t + R * uu;
-        const int io = (m + dly) & (N - 1);
-        const float2 a = FIELD == 0 ? mine : other, b = FIELD == 0 ? other : mine;
-        if (io < out_ny) sb_st_stream(dst + sb::gbuf_index(m, kx, kpitch), sb::gbuf_pack<float2, float4>(a, b));
+        for (int u = 0; u < R / 2; ++u) {
+            const int uu = u + HALF * (R / 2);
+            const float2 mine = x[slot(uu)];
+            const float2 other = xch_partner[uu * R + t];
+            sb_st_stream(p, sb::gbuf_pack<float2, float4>(FIELD == 0 ? mine : other, FIELD == 0 ? other : mine));
+            p += step;
+        }
+    } else {
+        const int io0 = t + dly + HALF * (R / 2) * R;
+#pragma unroll
+        for (int u = 0; u < R / 2; ++u) {
+            const int uu = u + HALF * (R / 2);
+            const float2 mine = x[slot(uu)];
+            const float2 other = xch_partner[uu * R + t];
+            const float4 v = sb::gbuf_pack<float2, float4>(FIELD == 0 ? mine : other, FIELD == 0 ? other : mine);
+            if (((io0 + u * R) & (N - 1)) < out_ny) sb_st_stream(p, v);
+            p += step;
+        }
     }
 }
 

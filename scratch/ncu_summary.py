@@ -24,7 +24,7 @@ METRICS = [
 
 
 def short(name):
-    m = re.match(r"(?:void )?(?:sb::)?(\w+)(<[^>]*>)?", name)
+    m = re.match(r"(?:void )?(?:\w+::)*(\w+)(<[^>]*>)?", name)
     return (m.group(1) + (m.group(2) or "")) if m else name
 
 
