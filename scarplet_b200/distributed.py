@@ -136,6 +136,39 @@ def merge_best_bands(plan, device, group=None, state=0):
     return lo, hi
 
 
+def set_dem_sharded(plan, z, device, group=None):
+    """``plan.set_dem(z)`` for an orientation-sharded search, where every rank needs the whole
+    raster: rank r copies only rows ``shard_bounds(ny, world, r)`` host -> device and the ranks
+    all-gather the rest over NVLink (one NCCL all-gather, in place) -- 1 / world of the PCIe
+    traffic per rank.  ``z``: the same host float64 (ny, nx) raster on every rank, a NumPy array
+    or a CPU ``torch.Tensor`` (a page-locked tensor makes the copy fast and asynchronous; it must
+    not change before the search that follows has returned).  The device buffer stays with the
+    plan."""
+    import torch
+    import torch.distributed as dist
+    world, rank = _world(group)
+    ny, nx = plan.ny, plan.nx
+    if world == 1 or (plan.row_lo, plan.row_hi) != (0, ny):
+        plan.set_dem(z)
+        return
+    if not isinstance(z, torch.Tensor):
+        z = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float64))
+    if tuple(z.shape) != (ny, nx) or z.dtype != torch.float64 or z.device.type != "cpu" or not z.is_contiguous():
+        raise ValueError("DEM: expected a contiguous host float64 raster of shape %r" % ((ny, nx),))
+    per = -(-ny // world)                        # equal chunks for the all-gather; the tail is padding
+    buf = plan.__dict__.get("_dem_shared")
+    if buf is None or buf.device != torch.device(device):
+        buf = plan.__dict__["_dem_shared"] = torch.zeros((world * per, nx), dtype=torch.float64, device=device)
+    fence = _Fence(plan, device)
+    fence.plan_done()                            # kernels of the last search may still read the buffer
+    lo, hi = rank * per, min((rank + 1) * per, ny)
+    if hi > lo:
+        buf[lo:hi].copy_(z[lo:hi], non_blocking=True)
+    dist.all_gather_into_tensor(buf.view(-1), buf[rank * per:(rank + 1) * per].view(-1), group=group)
+    fence.torch_done()
+    plan.set_dem_device(buf.data_ptr())
+
+
 def sharded_search(plan, spec, scale, ages, angles, order="age_major", device=None,
                    group=None, finalize=True, merge="replicated"):
     """Run this rank's shard of the orientation search on ``plan`` (DEM already set), merge

@@ -252,6 +252,21 @@ class Plan(object):
         ages = np.atleast_1d(np.asarray(ages, dtype=np.float64))
         angles = np.asarray(angles, dtype=np.float64)
         scales = [scale] if np.ndim(scale) == 0 else list(scale)
+        # the records depend on the arguments and the plan's geometry only: a repeated search
+        # (the same templates on the next raster of this shape) reuses them (read-only)
+        key = (id(spec), tuple(float(s) for s in scales), ages.tobytes(), angles.tobytes(), order,
+               None if angle_slice is None else tuple(angle_slice),
+               None if template_share is None else tuple(template_share))
+        memo = self.__dict__.setdefault("_sweep_memo", [])
+        for k, sp, val in memo:
+            if k == key and sp is spec:
+                return val
+        val = self._build_sweep(spec, scales, ages, angles, order, angle_slice, template_share)
+        memo.append((key, spec, val))
+        del memo[:-4]
+        return val
+
+    def _build_sweep(self, spec, scales, ages, angles, order, angle_slice, template_share):
         A, G = len(angles), len(ages)
         lo, hi = (0, A) if angle_slice is None else angle_slice
         t_lo = t_hi = None

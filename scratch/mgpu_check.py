@@ -64,12 +64,19 @@ def main():
                     plan.reset()
                     plan.sweep(a, t)
                     single = plan.finalize(age_of, angle_of)
+                    # DEM uploaded 1 / world per rank + all-gather (twice: the device buffer is reused)
+                    for _ in range(2):
+                        D.set_dem_sharded(plan, z, device)
+                        lo2, hi2, band2 = D.sharded_search(plan, spec, scale, ages, angles, device=device, merge="bands")
                 banded = gather_bands(band, lo, hi, n, n, device, rank, world)
+                banded2 = gather_bands(band2, lo2, hi2, n, n, device, rank, world)
             same = np.array_equal(merged, single)
             same_b = np.array_equal(banded, single)
-            ok &= same and same_b
-            print("rank %d %s %dx%d own_stream=%s: replicated == single: %s, banded == single: %s (valid px %d)"
-                  % (rank, name, n, n, own_stream, same, same_b, int((single[3] > 0).sum())), flush=True)
+            same_u = np.array_equal(banded2, single)
+            ok &= same and same_b and same_u
+            print("rank %d %s %dx%d own_stream=%s: replicated == single: %s, banded == single: %s, "
+                  "banded after the shared upload == single: %s (valid px %d)"
+                  % (rank, name, n, n, own_stream, same, same_b, same_u, int((single[3] > 0).sum())), flush=True)
         # rows sharded: host DEM
         plan, (lo, hi) = D.spatial_plan(n, n, 1.0, 1.0, spec, scale, ages, angles, device=local)
         with plan:

@@ -48,6 +48,18 @@ def _worker(rank, world, port, out_dir):
                                         merge="bands")
         assert (lo, hi) == D.shard_bounds(ny, world, rank) and band.shape == (4, hi - lo, nx)
         np.save(os.path.join(out_dir, "bands%d.npy" % rank), band)
+        # every rank uploads half of the rows, all-gather for the rest (twice: the buffer is reused)
+        for _ in range(2):
+            D.set_dem_sharded(plan, z, cpu)
+            lo, hi, band = D.sharded_search(plan, Scarp._sb_spec, SCALE, AGES, angles, "age_major", device=cpu,
+                                            merge="bands")
+        np.save(os.path.join(out_dir, "bands_shared_upload%d.npy" % rank), band)
+    # a row count the ranks do not divide: the last chunk of the all-gather is padded
+    with Plan(ny - 1, nx, 1.0, 1.0) as plan:
+        plan.set_dem(z[:-1])
+        a = plan.directional_laplacian(0.3)
+        D.set_dem_sharded(plan, z[:-1], cpu)
+        assert np.array_equal(plan.directional_laplacian(0.3), a, equal_nan=True)
     plan, (lo, hi) = D.spatial_plan(ny, nx, 1.0, 1.0, Scarp._sb_spec, SCALE, AGES, angles)
     with plan:
         plan.set_dem(z)
@@ -77,6 +89,8 @@ def test_two_rank_searches_equal_single_rank(tmp_path, emu_lib):
     r1 = np.load(tmp_path / "replicated1.npy")
     assert np.array_equal(r0, r1) and np.array_equal(r0, single)
     bands = np.concatenate([np.load(tmp_path / ("bands%d.npy" % r)) for r in range(2)], axis=1)
+    assert np.array_equal(bands, single)
+    bands = np.concatenate([np.load(tmp_path / ("bands_shared_upload%d.npy" % r)) for r in range(2)], axis=1)
     assert np.array_equal(bands, single)
     spatial = np.concatenate([np.load(tmp_path / ("spatial%d.npy" % r)) for r in range(2)], axis=1)
     rep = stack_report(spatial, single)
