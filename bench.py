@@ -438,7 +438,7 @@ def run_ours(args):
         # the row band it owns afterwards -- the distributed form of the (4, ny, nx) result
         e2e = None
         if not wl.get("device_dem"):
-            shared_upload = world > 1 and not rows_mode
+            shared_upload = world > 1 and not rows_mode and os.environ.get("SB_BENCH_SHARED_UPLOAD", "1") != "0"
 
             def e2e_step():
                 if shared_upload:      # H2D of 1 / world of the rows per rank + all-gather over NVLink
@@ -452,13 +452,19 @@ def run_ours(args):
 
             for _ in range(3):      # untimed: the plan's page-locked result pool fills (engine._result_array)
                 out = e2e_step()
+            # enough steps for ~1.3 s of timed work (short multi-GPU steps are sensitive to single
+            # host hiccups), at least 2, at most 10
+            e2e_steps = args.e2e_steps or int(min(10, max(2, -(-1300.0 // ms_step))))
             fence()
             t0 = time.perf_counter()
             out = None
-            for _ in range(args.e2e_steps):
+            marks = []
+            for _ in range(e2e_steps):
                 out = e2e_step()
+                marks.append(time.perf_counter())
             fence()
-            e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+            e2e_s = (time.perf_counter() - t0) / e2e_steps
+            step_ms = [round((b - a) * 1e3, 2) for a, b in zip([t0] + marks[:-1], marks)]
             t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
             h2d_dem = z_pinned.numel() * 8
             if shared_upload:
@@ -470,7 +476,7 @@ def run_ours(args):
                 dist.all_reduce(io, op=dist.ReduceOp.SUM)
             e2e = {"value": evals_per_step / float(t_e2e.item()) / 1e6, "unit": UNIT,
                    "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
-                   "ms_per_step": float(t_e2e.item()) * 1e3, "steps": args.e2e_steps,
+                   "ms_per_step": float(t_e2e.item()) * 1e3, "steps": e2e_steps, "rank0_step_ms": step_ms,
                    "api": "per rank: %s + distributed.%s -> (row_lo, row_hi, (4, rows, nx) float64 on host); "
                           "the ranks' row bands together are the (4, ny, nx) result"
                           % ("distributed.set_dem_sharded(host: 1 / world of the rows over PCIe, all-gather)" if shared_upload
@@ -618,7 +624,7 @@ def main():
     ap.add_argument("--shard", default=None, choices=["orientations", "rows"])
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--ages", type=int, default=None)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--profile-steps", type=int, default=None, help="steps of the per-kernel timing pass (default: --steps; 0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
