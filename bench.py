@@ -450,8 +450,52 @@ def run_ours(args):
                     return D.spatial_search(plan, spec, scale_arg, ages, angles)
                 return D.sharded_search(plan, spec, scale_arg, ages, angles, "age_major", device=device, merge="bands")
 
-            for _ in range(3):      # untimed: the plan's page-locked result pool fills (engine._result_array)
-                out = e2e_step()
+            for _ in range(5 if world > 1 else 3):   # untimed: the plan's page-locked result pool fills
+                out = e2e_step()                     # (engine._result_array), NCCL connects its channels
+            phases = None
+            if args.e2e_phases and not rows_mode:
+                # diagnostic (untimed, not the e2e number): where one e2e step spends its time on this
+                # rank -- host clock after a stream synchronise at the end of each phase
+                acc = np.zeros(5)
+                for _ in range(4):
+                    if world > 1:
+                        dist.barrier()
+                    fence()
+                    t = [time.perf_counter()]
+                    if shared_upload:
+                        D.set_dem_sharded(plan, z_pinned, device)
+                    else:
+                        plan.set_dem(z_pinned.numpy())
+                    stream.synchronize(); t.append(time.perf_counter())
+                    a_s, t_s, age_s, angle_s = plan.build_sweep(spec, scale_arg, ages, angles, "age_major",
+                                                               template_share=(rank, world))
+                    plan.reset()
+                    plan.sweep(a_s, t_s)
+                    stream.synchronize(); t.append(time.perf_counter())
+                    band = D.merge_best_bands(plan, device) if world > 1 else (0, n)
+                    stream.synchronize(); t.append(time.perf_counter())
+                    out = plan.finalize(age_s, angle_s, rows=band)
+                    stream.synchronize(); t.append(time.perf_counter())
+                    if world > 1:
+                        dist.barrier()
+                    t.append(time.perf_counter())
+                    acc += np.diff(t) * 1e3
+                acc /= 4
+                ph = torch.tensor(acc, dtype=torch.float64, device=device)
+                ph_max = ph.clone()
+                if world > 1:
+                    dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(ph, op=dist.ReduceOp.MIN)
+                names = ("upload", "sweep", "merge", "decode_download", "wait_for_ranks")
+                phases = {k: [round(float(a), 2), round(float(b), 2)] for k, a, b in zip(names, ph.tolist(), ph_max.tolist())}
+                by_rank = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+                mine = torch.tensor([acc[1]], dtype=torch.float64, device=device)
+                if world > 1:
+                    dist.all_gather(by_rank, mine)
+                else:
+                    by_rank = [mine]
+                phases["sweep_by_rank"] = [round(float(v.item()), 2) for v in by_rank]
+                phases["templates_by_rank"] = "SB_SHARE_BALANCE=%s" % os.environ.get("SB_SHARE_BALANCE", "cost")
             # enough steps for ~1.3 s of timed work (short multi-GPU steps are sensitive to single
             # host hiccups), at least 2, at most 10
             e2e_steps = args.e2e_steps or int(min(10, max(2, -(-1300.0 // ms_step))))
@@ -477,6 +521,7 @@ def run_ours(args):
             e2e = {"value": evals_per_step / float(t_e2e.item()) / 1e6, "unit": UNIT,
                    "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
                    "ms_per_step": float(t_e2e.item()) * 1e3, "steps": e2e_steps, "rank0_step_ms": step_ms,
+                   "phases_ms_min_max_over_ranks": phases,
                    "api": "per rank: %s + distributed.%s -> (row_lo, row_hi, (4, rows, nx) float64 on host); "
                           "the ranks' row bands together are the (4, ny, nx) result"
                           % ("distributed.set_dem_sharded(host: 1 / world of the rows over PCIe, all-gather)" if shared_upload
@@ -628,6 +673,7 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=None, help="steps of the per-kernel timing pass (default: --steps; 0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--e2e-phases", action="store_true", help="diagnostic: untimed per-phase host clock of an e2e step")
     ap.add_argument("--fast", type=int, default=None, help="developer switch: 0 = simple kernels")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -257,11 +257,14 @@ class Plan(object):
         key = (id(spec), tuple(float(s) for s in scales), ages.tobytes(), angles.tobytes(), order,
                None if angle_slice is None else tuple(angle_slice),
                None if template_share is None else tuple(template_share))
-        memo = self.__dict__.setdefault("_sweep_memo", [])
+        memo = getattr(self, "_sweep_memo", None)
+        if memo is None:
+            memo = []
+            setattr(self, "_sweep_memo", memo)
         for k, sp, val in memo:
             if k == key and sp is spec:
                 return val
-        val = self._build_sweep(spec, scales, ages, angles, order, angle_slice, template_share)
+        val = Plan._build_sweep(self, spec, scales, ages, angles, order, angle_slice, template_share)
         memo.append((key, spec, val))
         del memo[:-4]
         return val
@@ -270,16 +273,15 @@ class Plan(object):
         A, G = len(angles), len(ages)
         lo, hi = (0, A) if angle_slice is None else angle_slice
         t_lo = t_hi = None
+        ai, gi = np.meshgrid(np.arange(A), np.arange(G), indexing="ij")
         if template_share is not None:
             rank, world = template_share
             per_angle = G * len(scales)
-            base, extra = divmod(A * per_angle, world)
-            t_lo = rank * base + min(rank, extra)
-            t_hi = t_lo + base + (1 if rank < extra else 0)
+            cuts = Plan._share_cuts(self, spec, scales, ages, angles, world)
+            t_lo, t_hi = int(cuts[rank]), int(cuts[rank + 1])
             lo, hi = t_lo // per_angle, -(-t_hi // per_angle)
             if t_hi == t_lo:
                 lo = hi = 0
-        ai, gi = np.meshgrid(np.arange(A), np.arange(G), indexing="ij")
         idx = gi * A + ai if order == "age_major" else ai * G + gi          # [A, G]
         age_of = np.empty(A * G, dtype=np.float64)
         angle_of = np.empty(A * G, dtype=np.float64)
@@ -303,6 +305,34 @@ class Plan(object):
             whole = (c_int * 5)(min(e[0] for e in ext), max(e[1] for e in ext), min(e[2] for e in ext),
                                 max(e[3] for e in ext), G * len(scales))
         return (arr_a, hi - lo), (arr_t, len(recs), whole), age_of, angle_of
+
+    # relative device time of the per-template kernels in a many-ages search (C3 on one B200:
+    # column kernel 338 ms, fit kernel 276 ms, template rows 24 ms of a 643 ms step)
+    SHARE_COST = (0.53, 0.43, 0.04)
+
+    def _share_cuts(self, spec, scales, ages, angles, world):
+        """Cut points [world + 1] of the orientation-major template list into contiguous shares of
+        equal estimated device time.  The column kernel costs the same for every template; the
+        fit kernel works on the rows of the template's un-masked window (3344 .. 4094 of 4096
+        rows at scale 100, by orientation) and the template kernel on the rows of its support
+        (9 .. 333): equal COUNTS leave the ranks of an 8-way C3 search 6 % apart.
+        ``SB_SHARE_BALANCE=count`` restores equal counts (shares differ by at most one template)."""
+        A, G, S = len(angles), len(ages), len(scales)
+        n = A * G * S
+        if os.environ.get("SB_SHARE_BALANCE", "cost") == "count" or n < 2 * world:
+            base, extra = divmod(n, world)
+            return np.array([r * base + min(r, extra) for r in range(world + 1)], dtype=np.int64)
+        zero = np.zeros((A, G), dtype=np.int64)
+        recs = [P.template_records(spec, sc, ages, angles, self.nx, self.ny, self.dx, self.x, self.y,
+                                   np.arange(A), zero, state=k) for k, sc in enumerate(scales)]
+        recs = np.stack(recs, axis=1).reshape(-1)                                        # [angle][scale][age]
+        rows = np.maximum(recs["i_hi"] - recs["i_lo"] + 1, 0).astype(np.float64)
+        sup = np.maximum(recs["sy_hi"] - recs["sy_lo"] + 1, 1).astype(np.float64)
+        c_col, c_fit, c_tmpl = Plan.SHARE_COST
+        cost = c_col + c_fit * rows / max(rows.mean(), 1.0) + c_tmpl * sup / sup.mean()
+        mid = np.cumsum(cost) - 0.5 * cost                       # a template goes to the share its midpoint falls into
+        share = np.minimum((mid / cost.sum() * world).astype(np.int64), world - 1)
+        return np.searchsorted(share, np.arange(world + 1), side="left").astype(np.int64)
 
     def reset(self):
         check(self.lib, self.lib.sb_best_reset(self._h))

@@ -183,18 +183,23 @@ def test_bulk_template_records_equal_single(ny, nx, de, cls, scale, ages):
     assert arr[G + 1].idx == idx[1, 1 % G] if G > 1 else arr[1].idx == idx[1, 0]
 
 
-def test_template_shares_partition_the_search():
+def test_template_shares_partition_the_search(monkeypatch):
     """``build_sweep(template_share=(rank, world))``: the ranks' records are a partition of the
-    whole search (orientation-major), sizes differ by at most one template, indices unchanged."""
+    whole search (orientation-major, contiguous), indices unchanged; shares of equal estimated
+    device time by default (a few per cent apart in count), of equal count (+- 1 template) with
+    ``SB_SHARE_BALANCE=count``."""
+    from scarplet_b200.engine import Plan
+
     class FakePlan(object):
         nx, ny, dx = 64, 64, 1.0
         x, y = P.axis_vectors(64, 64, 1.0)
-    from scarplet_b200.engine import Plan
     angles = P.search_angles(-np.pi / 2, np.pi / 2)
     ages = np.logspace(0, 3.5, 30)
     _, (full, n_full, _w), age_of, angle_of = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major")
     assert n_full == 181 * 30 * 2
-    for world in (1, 2, 8, 7):
+    for world, mode in ((1, "cost"), (2, "cost"), (8, "cost"), (7, "cost"), (8, "count"), (7, "count")):
+        monkeypatch.setenv("SB_SHARE_BALANCE", mode)
+        FakePlan._sweep_memo = []
         seen, sizes = [], []
         for rank in range(world):
             (a, na), (t, nt, _w), _, _ = Plan.build_sweep(FakePlan, T.Scarp._sb_spec, [8, 12], ages, angles, "age_major",
@@ -205,5 +210,7 @@ def test_template_shares_partition_the_search():
                 seen.append((t[k].idx, t[k].state, round(angle_of[t[k].idx], 12)))
                 # the angle record the template points at is its own orientation
                 assert np.isclose(a[t[k].angle_id].cos_a, np.cos(angle_of[t[k].idx]))
-        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n_full
+        assert sum(sizes) == n_full and min(sizes) > 0
+        if mode == "count":
+            assert max(sizes) - min(sizes) <= 1
         assert seen == [(full[k].idx, full[k].state, round(angle_of[full[k].idx], 12)) for k in range(n_full)]
