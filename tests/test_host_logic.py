@@ -214,3 +214,23 @@ def test_template_shares_partition_the_search(monkeypatch):
         if mode == "count":
             assert max(sizes) - min(sizes) <= 1
         assert seen == [(full[k].idx, full[k].state, round(angle_of[full[k].idx], 12)) for k in range(n_full)]
+
+
+def test_share_cuts_edge_cases(monkeypatch):
+    """``Plan._share_cuts``: monotone cut points from 0 to the number of templates for any world
+    size -- more ranks than templates leaves some shares empty, never a template unassigned."""
+    from scarplet_b200.engine import Plan
+
+    class FakePlan(object):
+        nx, ny, dx = 200, 160, 1.0
+        x, y = P.axis_vectors(200, 160, 1.0)
+    angles = P.search_angles(-np.pi / 2, np.pi / 2)
+    for mode in ("cost", "count"):
+        monkeypatch.setenv("SB_SHARE_BALANCE", mode)
+        for n_angles, ages, world in ((181, [10.0], 8), (181, [1.0, 100.0, 3000.0], 5), (3, [10.0], 8), (1, [10.0], 2),
+                                      (181, np.logspace(0, 3.5, 30), 1)):
+            cuts = Plan._share_cuts(FakePlan, T.Scarp._sb_spec, [20.0], np.asarray(ages), angles[:n_angles], world)
+            n = n_angles * len(ages)
+            assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == n and np.all(np.diff(cuts) >= 0), (mode, cuts)
+            if n >= 2 * world:
+                assert np.all(np.diff(cuts) > 0)
