@@ -74,9 +74,15 @@ int sb_plan_create(sb_plan** plan, int ny, int nx, double dx, double dx2, double
                    int device, void* stream, unsigned flags);
 int sb_plan_destroy(sb_plan* plan);
 
-/* knobs: key in {"workspace_mb", "max_fft", "force_pad", "mixed_tiles", "profile", "conv_persist",
+/* knobs: key in {"workspace_mb", "max_fft", "force_pad", "mixed_tiles", "profile",
  * "precision" (32 = complex64 pipeline, default; 64 = complex128 pipeline),
- * "states" (number of independent best states, default 1; resets them)}; returns 0 if known */
+ * "states" (number of independent best states, default 1; resets them),
+ * and the kernel-selection switches, all on by default (off = the slower variant, same results
+ * to rounding): "fast" (pipelined complex64 kernels), "conv_persist" (persistent column kernel:
+ * minimum templates per orientation run, 0 = never), "conv_r64" (radix-64 column kernel at
+ * Py = 4096), "lincomb" (curvature spectra as combinations of nine plane spectra),
+ * "fit_substreams" (0 = automatic, 1..8 = sub-streams of the row kernel on small rasters)};
+ * returns 0 if known */
 int sb_plan_set_option(sb_plan* plan, const char* key, long value);
 
 /* Spatial sharding of one raster over several GPUs (BASELINE config 5; the reference's
